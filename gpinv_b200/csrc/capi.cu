@@ -1,0 +1,139 @@
+// extern "C" surface of libgpinv_sm100.so (declared in include/gpinv_b200.h).
+#include <cstring>
+#include <string>
+
+#include "../../include/gpinv_b200.h"
+#include "gemm.cuh"
+
+namespace gpinv {
+static thread_local std::string g_last_error;
+void set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }
+
+// implemented in the other translation units
+size_t kbuild_ws_bytes(int n, int n2, int D);
+int kbuild_f64(const double*, const double*, int, int, int, int, int, const double*, int, int,
+               double, double*, int, double*, cudaStream_t);
+int kbuild_bwd_f64(const double*, const double*, int, int, int, int, int, const double*, int, int,
+                   const double*, int, double*, double*, cudaStream_t);
+int potrf_f64(double*, int, int, int*, cudaStream_t);
+size_t potrf_bwd_ws_bytes(int);
+int potrf_bwd_f64(const double*, int, double*, int, int, double*, cudaStream_t);
+int trsm_rlt_f64(const double*, int, double*, int, int, int, cudaStream_t);
+int tril_unpack_f64(const double*, double*, int, int, cudaStream_t);
+int tril_pack_f64(const double*, double*, int, int, cudaStream_t);
+int sumsq_f64(const double*, size_t, double*, cudaStream_t);
+int sample_fwd_f64(const double*, int, const double*, const double*, int, const double*,
+                   const double*, const double*, int, int, int, double*, double*, double*, double*,
+                   cudaStream_t);
+int sample_bwd_f64(const double*, int, const double*, const double*, int, const double*,
+                   const double*, const double*, const double*, int, int, int, double*, double*,
+                   double*, double*, int, double*, double*, cudaStream_t);
+int gauss_sumsq_f64(const double*, const double*, int, int, int, double*, cudaStream_t);
+int gauss_bwd_f64(const double*, const double*, int, int, int, const double*, double*,
+                  cudaStream_t);
+int abel_fwd_f64(const double*, const double*, int, const double*, int, int, int, double*, double*,
+                 cudaStream_t);
+int abel_bwd_f64(const double*, const double*, int, const double*, const double*, int, int, int,
+                 double*, cudaStream_t);
+}  // namespace gpinv
+
+using namespace gpinv;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int gpinv_version(void) { return 100; }
+const char* gpinv_last_error(void) { return g_last_error.c_str(); }
+
+size_t gpinv_kbuild_ws_bytes(int n, int n2, int D) { return kbuild_ws_bytes(n, n2, D); }
+
+int gpinv_kbuild_f64(const double* X, const double* X2, int n, int n2, int D, int ldx, int ldx2,
+                     const double* ls, int ard, int mode, double jitter, double* K, int ldk,
+                     void* ws, void* stream) {
+  return kbuild_f64(X, X2, n, n2, D, ldx, ldx2, ls, ard, mode, jitter, K, ldk,
+                    static_cast<double*>(ws), ST(stream));
+}
+
+int gpinv_kbuild_bwd_f64(const double* X, const double* X2, int n, int n2, int D, int ldx,
+                         int ldx2, const double* ls, int ard, int mode, const double* Kbar,
+                         int ldkb, double* ls_bar, void* ws, void* stream) {
+  return kbuild_bwd_f64(X, X2, n, n2, D, ldx, ldx2, ls, ard, mode, Kbar, ldkb, ls_bar,
+                        static_cast<double*>(ws), ST(stream));
+}
+
+int gpinv_potrf_f64(double* A, int n, int lda, int* info, void* stream) {
+  if (n <= 0 || lda < n) return GPINV_ERR_ARG;
+  return potrf_f64(A, n, lda, info, ST(stream));
+}
+
+size_t gpinv_potrf_bwd_ws_bytes(int n) { return potrf_bwd_ws_bytes(n); }
+
+int gpinv_potrf_bwd_f64(const double* L, int ldl, double* Abar, int ldab, int n, void* ws,
+                        void* stream) {
+  if (n <= 0 || ldl < n || ldab < n) return GPINV_ERR_ARG;
+  return potrf_bwd_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
+}
+
+int gpinv_trsm_rlt_f64(const double* L, int ldl, double* X, int ldx, int m, int n, void* stream) {
+  if (n <= 0 || ldl < n || ldx < n) return GPINV_ERR_ARG;
+  return trsm_rlt_f64(L, ldl, X, ldx, m, n, ST(stream));
+}
+
+int gpinv_gemm_f64(int transa, int transb, int m, int n, int k, double alpha, const double* A,
+                   int lda, const double* B, int ldb, double beta, double* C, int ldc, int lower,
+                   void* stream) {
+  // row-major: op(A) is m x k.  'N': A stored m x k (k contiguous -> LK);  'T': stored k x m (LMN).
+  // op(B) is k x n.  'N': B stored k x n (n contiguous -> LMN);  'T': stored n x k (LK).
+  const int la = transa ? LMN : LK;
+  const int lb = transb ? LK : LMN;
+  return gemm_simple(la, lb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower != 0, 0, 1,
+                     ST(stream));
+}
+
+int gpinv_tril_unpack_f64(const double* src, double* dst, int n, int R, void* stream) {
+  return tril_unpack_f64(src, dst, n, R, ST(stream));
+}
+int gpinv_tril_pack_f64(const double* src, double* dst, int n, int R, void* stream) {
+  return tril_pack_f64(src, dst, n, R, ST(stream));
+}
+
+int gpinv_sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q,
+                         int q_diag, const double* q_mu, const double* mean, const double* E,
+                         int n, int S, int R, double* U, double* F, double* expF, double* kl_out,
+                         void* stream) {
+  return sample_fwd_f64(Lc, ldl, sqrt_v, Q, q_diag, q_mu, mean, E, n, S, R, U, F, expF, kl_out,
+                        ST(stream));
+}
+
+int gpinv_sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q,
+                         int q_diag, const double* E, const double* U, const double* Fbar,
+                         const double* klbar, int n, int S, int R, double* Ubar, double* qmu_bar,
+                         double* Qbar, double* Lc_bar, int ldlb, double* svdot, double* mean_bar,
+                         void* stream) {
+  return sample_bwd_f64(Lc, ldl, sqrt_v, Q, q_diag, E, U, Fbar, klbar, n, S, R, Ubar, qmu_bar,
+                        Qbar, Lc_bar, ldlb, svdot, mean_bar, ST(stream));
+}
+
+int gpinv_gauss_sumsq_f64(const double* F, const double* Y, int n, int S, int R, double* out,
+                          void* stream) {
+  return gauss_sumsq_f64(F, Y, n, S, R, out, ST(stream));
+}
+int gpinv_gauss_bwd_f64(const double* F, const double* Y, int n, int S, int R, const double* coef,
+                        double* Fbar, void* stream) {
+  return gauss_bwd_f64(F, Y, n, S, R, coef, Fbar, ST(stream));
+}
+
+int gpinv_abel_fwd_f64(const double* expF, const double* A, int lda, const double* Y, int n, int M,
+                       int S, double* Rs, double* sumsq, void* stream) {
+  return abel_fwd_f64(expF, A, lda, Y, n, M, S, Rs, sumsq, ST(stream));
+}
+int gpinv_abel_bwd_f64(const double* Rs, const double* A, int lda, const double* expF,
+                       const double* coef, int n, int M, int S, double* Fbar, void* stream) {
+  return abel_bwd_f64(Rs, A, lda, expF, coef, n, M, S, Fbar, ST(stream));
+}
+
+int gpinv_sumsq_f64(const double* x, size_t count, double* out, void* stream) {
+  return sumsq_f64(x, count, out, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// Host-side dispatch for the DMMA GEMM template (see gemm.cuh).
+#include "gemm.cuh"
+
+#include <cstdio>
+#include <mutex>
+
+namespace gpinv {
+
+namespace {
+
+template <int LA, int LB, unsigned EF>
+int launch_inst(const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_dmma_kernel<LA, LB, EF>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         gemm_cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error(cudaGetErrorString(e));
+      return GPINV_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  kern<<<grid, gemm_cfg::THREADS, gemm_cfg::SMEM_BYTES, stream>>>(p);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+#define GPINV_GEMM_CASE(LA_, LB_, EF_)                                   \
+  if (la == (LA_) && lb == (LB_) && ef == (unsigned)(EF_))               \
+    return launch_inst<LA_, LB_, (unsigned)(EF_)>(p, grid, stream);
+
+#define GPINV_GEMM_GENERIC(LA_, LB_)                      \
+  GPINV_GEMM_CASE(LA_, LB_, EF_BETA)                      \
+  GPINV_GEMM_CASE(LA_, LB_, EF_BETA | EF_LOWER)           \
+  GPINV_GEMM_CASE(LA_, LB_, EF_ATOMIC)                    \
+  GPINV_GEMM_CASE(LA_, LB_, EF_ATOMIC | EF_LOWER)
+
+int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) {
+  using namespace gemm_cfg;
+  if (p.M <= 0 || p.N <= 0) return GPINV_OK;
+  if (p.splitk < 1) p.splitk = 1;
+  if (p.splitk > 1 && !(ef & EF_ATOMIC)) {
+    set_last_error("gemm: split-K requires the atomic epilogue");
+    return GPINV_ERR_ARG;
+  }
+  p.tiles_m = cdiv(p.M, BM);
+  p.tiles_n = cdiv(p.N, BN);
+  if ((ef & EF_LOWER) && p.tiles_m != p.tiles_n) {
+    set_last_error("gemm: lower-triangular output must be square");
+    return GPINV_ERR_ARG;
+  }
+  p.vecA = aligned16(p.A) && (p.lda % 2 == 0);
+  p.vecB = aligned16(p.B) && (p.ldb % 2 == 0);
+  p.vecO = (p.out == nullptr) || (aligned16(p.out) && (p.ldo % 2 == 0));
+  const int ntiles = (ef & EF_LOWER) ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
+  if (p.batch < 1) p.batch = 1;
+  if (p.batch > 1) {
+    p.vecA = p.vecA && (p.strideA % 2 == 0);
+    p.vecB = p.vecB && (p.strideB % 2 == 0);
+    p.vecO = p.vecO && (p.strideO % 2 == 0);
+  }
+  dim3 grid(ntiles, p.splitk, p.batch);
+
+  GPINV_GEMM_GENERIC(LK, LK)
+  GPINV_GEMM_GENERIC(LK, LMN)
+  GPINV_GEMM_GENERIC(LMN, LMN)
+  GPINV_GEMM_GENERIC(LMN, LK)
+  // fused epilogues of the StVGP sample / Abel stages
+  GPINV_GEMM_CASE(LK, LK, EF_COLVEC | EF_SUMSQ)               // U = E Q^T + m ; R = Y - X A^T
+  GPINV_GEMM_CASE(LK, LK, EF_COLVEC)                          // F = sv U Lc^T + mu
+  GPINV_GEMM_CASE(LK, LK, EF_COLVEC | EF_EXP2)                // ... and exp(F)
+  GPINV_GEMM_CASE(LK, LMN, EF_MULMAT)                         // Fbar = X o (R A) c
+  GPINV_GEMM_CASE(LK, LMN, EF_BETA | EF_COLSUM)               // Ubar = sv Fbar Lc + klbar U
+  GPINV_GEMM_CASE(LMN, LMN, EF_LOWER)                         // Qbar = tril(Ubar^T E)
+  GPINV_GEMM_CASE(LMN, LMN, EF_LOWER | EF_BETA | EF_DOT)      // Lbar += tril(Fbar^T U), <.,Lc>
+  set_last_error("gemm: no kernel instantiated for this layout / epilogue combination");
+  return GPINV_ERR_ARG;
+}
+
+int gemm_simple(int la, int lb, int M, int N, int K, double alpha, const double* A, int lda,
+                const double* B, int ldb, double beta, double* C, int ldc, bool lower, int kmode,
+                int splitk, cudaStream_t stream) {
+  GemmParams p = {};
+  p.A = A; p.B = B; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb;
+  p.alpha = alpha; p.beta = beta; p.Cin = C; p.ldcin = ldc; p.out = C; p.ldo = ldc;
+  p.kmode = kmode; p.splitk = splitk;
+  unsigned ef = (splitk > 1) ? EF_ATOMIC : EF_BETA;
+  if (lower) ef |= EF_LOWER;
+  if (splitk > 1 && beta != 1.0) {
+    set_last_error("gemm_simple: split-K needs beta == 1");
+    return GPINV_ERR_ARG;
+  }
+  return gemm_launch(la, lb, ef, p, stream);
+}
+
+}  // namespace gpinv

@@ -1,0 +1,333 @@
+// FP64 tensor-core (DMMA.8x8x4) GEMM with fused epilogues, triangular k-range skipping,
+// lower-triangular output and split-K.  One kernel template serves every GEMM-shaped stage
+// of the StVGP/GPMC hot path (sample products T10/T12, Abel transform T15, their reverse
+// products, and the trailing updates of the blocked Cholesky T4 and its reverse sweep).
+//
+//   out(r,c) = epilogue( alpha * sum_k A(r,k) * B(c,k) ),  r < M, c < N, k in [k_begin,k_end)
+//
+// Operand layouts:  LK  : element (r,k) at p[r*ld + k]   (k contiguous)
+//                   LMN : element (r,k) at p[k*ld + r]   (row index contiguous)
+// so BLAS "C = A B^T" is <LK,LK>, "C = A B" is <LK,LMN>, "C = A^T B" is <LMN,LMN>.
+//
+// CTA tile 128x128x16, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA tiles, accumulators in
+// registers (128 regs), 4-stage cp.async (LDGSTS) pipeline, padded conflict-free smem.
+#pragma once
+#include "common.cuh"
+
+namespace gpinv {
+
+enum Layout { LK = 0, LMN = 1 };
+
+enum : unsigned {
+  EF_BETA = 1u,     // v += beta * Cin(r,c)
+  EF_COLVEC = 2u,   // v += colvec[c]
+  EF_MULMAT = 4u,   // v *= Mul(r,c)
+  EF_EXP2 = 8u,     // out2(r,c) = exp(v)
+  EF_SUMSQ = 16u,   // *sumsq += sum v^2
+  EF_COLSUM = 32u,  // colsum[c] += sum_r v
+  EF_DOT = 64u,     // *dot += sum (alpha*acc) * W(r,c)
+  EF_LOWER = 128u,  // square output, only c <= r computed / stored
+  EF_ATOMIC = 256u  // split-K: out(r,c) += alpha*acc via red.add.f64
+};
+
+struct GemmParams {
+  const double* A;
+  const double* B;
+  int M, N, K;
+  int lda, ldb;
+  double alpha;
+  const double* alpha_dev;  // optional device scalar multiplied into alpha
+  double beta;
+  const double* beta_dev;  // optional device scalar multiplied into beta
+  const double* Cin;
+  int ldcin;
+  double* out;  // may be null (then only out2 / reductions are produced)
+  int ldo;
+  double* out2;
+  int ldo2;
+  const double* colvec;
+  const double* mul;
+  int ldmul;
+  const double* W;
+  int ldw;
+  double* sumsq;
+  double* colsum;
+  double* dot;
+  int kmode;   // 0 full | 1: k < n0+BN | 2: k >= n0 | 3: k < m0+BM | 4: k >= m0
+  int splitk;  // >= 1
+  int tiles_m, tiles_n;
+  int vecA, vecB, vecO;  // 16-byte alignment of operands / output rows
+  // batching over blockIdx.z (element strides; 0 = shared operand)
+  int batch;
+  long long strideA, strideB, strideO, strideCin;
+};
+
+namespace gemm_cfg {
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int THREADS = 256;
+constexpr int STAGES = 4;
+constexpr int LDK = BK + 4;     // LK   tile: [128][20]
+constexpr int LDM = BM + 4;     // LMN  tile: [16][132]
+constexpr int TILE_ELEMS = BM * LDK;  // 2560 doubles >= 16*132 = 2112
+constexpr int STAGE_ELEMS = 2 * TILE_ELEMS;
+constexpr int SMEM_BYTES = STAGES * STAGE_ELEMS * 8;  // 163840
+}  // namespace gemm_cfg
+
+template <int LAYOUT>
+__device__ __forceinline__ void gemm_load_tile(double* s, const double* __restrict__ g, int ld,
+                                               int r0, int k0, int Rmax, int Kmax, int vec,
+                                               int tid) {
+  using namespace gemm_cfg;
+  if (LAYOUT == LK) {
+    if (vec) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int id = tid + c * THREADS;
+        const int row = id >> 3, kc = (id & 7) * 2;
+        const int gr = r0 + row, gk = k0 + kc;
+        int valid = (gr < Rmax) ? min(max(Kmax - gk, 0), 2) : 0;
+        const double* src = valid ? g + (size_t)gr * ld + gk : g;
+        cp_async16(s + row * LDK + kc, src, valid * 8);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int id = tid + c * THREADS;
+        const int row = id >> 4, k = id & 15;
+        const int gr = r0 + row, gk = k0 + k;
+        const bool ok = (gr < Rmax) && (gk < Kmax);
+        const double* src = ok ? g + (size_t)gr * ld + gk : g;
+        cp_async8(s + row * LDK + k, src, ok ? 8 : 0);
+      }
+    }
+  } else {
+    if (vec) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int id = tid + c * THREADS;
+        const int k = id >> 6, rc = (id & 63) * 2;
+        const int gr = r0 + rc, gk = k0 + k;
+        int valid = (gk < Kmax) ? min(max(Rmax - gr, 0), 2) : 0;
+        const double* src = valid ? g + (size_t)gk * ld + gr : g;
+        cp_async16(s + k * LDM + rc, src, valid * 8);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int id = tid + c * THREADS;
+        const int k = id >> 7, r = id & 127;
+        const int gr = r0 + r, gk = k0 + k;
+        const bool ok = (gr < Rmax) && (gk < Kmax);
+        const double* src = ok ? g + (size_t)gk * ld + gr : g;
+        cp_async8(s + k * LDM + r, src, ok ? 8 : 0);
+      }
+    }
+  }
+}
+
+template <int LA, int LB, unsigned EF>
+__global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const GemmParams pin) {
+  using namespace gemm_cfg;
+  extern __shared__ __align__(16) double smem[];
+  GemmParams p = pin;
+  if (p.batch > 1) {
+    const long long z = blockIdx.z;
+    p.A += z * p.strideA;
+    p.B += z * p.strideB;
+    if (p.out) p.out += z * p.strideO;
+    if (p.Cin) p.Cin += z * p.strideCin;
+  }
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+
+  // ---- tile decode (heavy tiles first so the hardware scheduler balances the tail) ----
+  int tm, tn;
+  {
+    const int idx = blockIdx.x;
+    if (EF & EF_LOWER) {
+      int r = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+      while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+      while (r * (r + 1) / 2 > idx) --r;
+      tm = r;
+      tn = idx - r * (r + 1) / 2;
+    } else if (p.kmode == 1) {
+      tn = p.tiles_n - 1 - idx / p.tiles_m;
+      tm = idx % p.tiles_m;
+    } else if (p.kmode == 3) {
+      tm = p.tiles_m - 1 - idx / p.tiles_n;
+      tn = idx % p.tiles_n;
+    } else if (p.kmode == 4) {
+      tm = idx / p.tiles_n;
+      tn = idx % p.tiles_n;
+    } else {
+      tn = idx / p.tiles_m;
+      tm = idx % p.tiles_m;
+    }
+  }
+  const int m0 = tm * BM, n0 = tn * BN;
+
+  // ---- k range ----
+  int kb = 0, ke = p.K;
+  if (p.kmode == 1) ke = min(p.K, n0 + BN);
+  else if (p.kmode == 2) kb = (n0 / BK) * BK;
+  else if (p.kmode == 3) ke = min(p.K, m0 + BM);
+  else if (p.kmode == 4) kb = (m0 / BK) * BK;
+  int ktiles = (ke > kb) ? (ke - kb + BK - 1) / BK : 0;
+  if (p.splitk > 1) {
+    const int per = (ktiles + p.splitk - 1) / p.splitk;
+    const int first = blockIdx.y * per;
+    const int last = min(ktiles, first + per);
+    kb += first * BK;
+    ktiles = max(last - first, 0);
+    if (ktiles == 0) return;
+  }
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // ---- pipeline prologue ----
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < ktiles) {
+      double* sA = smem + s * STAGE_ELEMS;
+      double* sB = sA + TILE_ELEMS;
+      gemm_load_tile<LA>(sA, p.A, p.lda, m0, kb + s * BK, p.M, ke, p.vecA, tid);
+      gemm_load_tile<LB>(sB, p.B, p.ldb, n0, kb + s * BK, p.N, ke, p.vecB, tid);
+    }
+    cp_async_commit();
+  }
+
+  // fragment base offsets inside a tile
+  const int aoff = (LA == LK) ? ((wm * 64 + g) * LDK + t) : (t * LDM + wm * 64 + g);
+  const int boff = (LB == LK) ? ((wn * 32 + g) * LDK + t) : (t * LDM + wn * 32 + g);
+  constexpr int A_ISTRIDE = (LA == LK) ? 8 * LDK : 8;   // next 8-row DMMA tile
+  constexpr int A_KSTRIDE = (LA == LK) ? 4 : 4 * LDM;   // next k4 step
+  constexpr int B_JSTRIDE = (LB == LK) ? 8 * LDK : 8;
+  constexpr int B_KSTRIDE = (LB == LK) ? 4 : 4 * LDM;
+
+  for (int kt = 0; kt < ktiles; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + STAGES - 1;
+      if (nk < ktiles) {
+        double* sA = smem + (nk % STAGES) * STAGE_ELEMS;
+        double* sB = sA + TILE_ELEMS;
+        gemm_load_tile<LA>(sA, p.A, p.lda, m0, kb + nk * BK, p.M, ke, p.vecA, tid);
+        gemm_load_tile<LB>(sB, p.B, p.ldb, n0, kb + nk * BK, p.N, ke, p.vecB, tid);
+      }
+      cp_async_commit();
+    }
+    const double* sA = smem + (kt % STAGES) * STAGE_ELEMS + aoff;
+    const double* sB = smem + (kt % STAGES) * STAGE_ELEMS + TILE_ELEMS + boff;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = sA[i * A_ISTRIDE + kk * A_KSTRIDE];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[j * B_JSTRIDE + kk * B_KSTRIDE];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue ----
+  double alpha = p.alpha;
+  if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
+  double beta = 0.0;
+  if (EF & EF_BETA) {
+    beta = p.beta;
+    if (p.beta_dev) beta *= __ldg(p.beta_dev);
+  }
+  double r_sumsq = 0.0, r_dot = 0.0;
+  double r_col[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r_col[j][0] = r_col[j][1] = 0.0;
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + wm * 64 + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + wn * 32 + j * 8 + 2 * t;
+      double v[2];
+      bool ok[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = col + e;
+        ok[e] = (row < p.M) && (c < p.N);
+        if (EF & EF_LOWER) ok[e] = ok[e] && (c <= row);
+        double x = alpha * acc[i][j][e];
+        if (ok[e]) {
+          if (EF & EF_DOT) r_dot += x * __ldg(p.W + (size_t)row * p.ldw + c);
+          if (EF & EF_MULMAT) x *= __ldg(p.mul + (size_t)row * p.ldmul + c);
+          if ((EF & EF_BETA) && beta != 0.0) x += beta * p.Cin[(size_t)row * p.ldcin + c];
+          if (EF & EF_COLVEC) x += __ldg(p.colvec + c);
+          if (EF & EF_SUMSQ) r_sumsq += x * x;
+          if (EF & EF_COLSUM) r_col[j][e] += x;
+        }
+        v[e] = x;
+      }
+      if (EF & EF_ATOMIC) {
+        if (ok[0]) atomicAdd(p.out + (size_t)row * p.ldo + col, v[0]);
+        if (ok[1]) atomicAdd(p.out + (size_t)row * p.ldo + col + 1, v[1]);
+      } else {
+        if (p.out) {
+          double* o = p.out + (size_t)row * p.ldo + col;
+          if (ok[0] && ok[1] && p.vecO) {
+            *reinterpret_cast<double2*>(o) = make_double2(v[0], v[1]);
+          } else {
+            if (ok[0]) o[0] = v[0];
+            if (ok[1]) o[1] = v[1];
+          }
+        }
+        if (EF & EF_EXP2) {
+          double* o = p.out2 + (size_t)row * p.ldo2 + col;
+          if (ok[0]) o[0] = exp(v[0]);
+          if (ok[1]) o[1] = exp(v[1]);
+        }
+      }
+    }
+  }
+  if (EF & EF_SUMSQ) {
+    r_sumsq = warp_sum(r_sumsq);
+    if (lane == 0) atomicAdd(p.sumsq, r_sumsq);
+  }
+  if (EF & EF_DOT) {
+    r_dot = warp_sum(r_dot);
+    if (lane == 0) atomicAdd(p.dot, r_dot);
+  }
+  if (EF & EF_COLSUM) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double s = r_col[j][e];
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        const int c = n0 + wn * 32 + j * 8 + 2 * t + e;
+        if (g == 0 && c < p.N) atomicAdd(p.colsum + c, s);
+      }
+  }
+}
+
+// Host-side launcher (defined in gemm.cu).  `la`,`lb` are Layout values, `ef` the flag set.
+int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream);
+
+// Convenience: C = alpha*op(A)op(B) + beta*C with optional lower-only output / k-range mode.
+int gemm_simple(int la, int lb, int M, int N, int K, double alpha, const double* A, int lda,
+                const double* B, int ldb, double beta, double* C, int ldc, bool lower, int kmode,
+                int splitk, cudaStream_t stream);
+
+}  // namespace gpinv

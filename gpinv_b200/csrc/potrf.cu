@@ -1,0 +1,582 @@
+// Blocked fp64 Cholesky (T4) and its reverse-mode sweep for sm_100a.
+//
+// Forward: two-level right-looking.  Outer panels of NBO columns get a DMMA SYRK trailing
+// update (K = NBO); inside a panel, 64-column sub-panels are factored by `panel_kernel`
+// (diagonal block potrf fused with the substitution-form TRSM of all rows below; every CTA
+// re-factors the 64x64 diagonal block in shared memory so there is no inter-CTA dependency)
+// followed by a K=64 DMMA update of the remaining panel columns.
+//
+// Reverse: Murray's level-3 blocked reverse sweep (arXiv:1602.07527, Alg. "blocked
+// reverse-mode"), two-level: NBO-wide outer steps whose GEMMs run on the DMMA kernel,
+// 64-wide inner steps with a substitution TRSM leaf and a level-2 leaf reverse in smem.
+// Replaces tf.cholesky + its CholeskyGrad op at GPinv/kernels.py:59 and
+// GPinv/kronecker.py:54,57 (reference /root/reference).
+#include <climits>
+
+#include "gemm.cuh"
+
+namespace gpinv {
+
+namespace pcfg {
+constexpr int NB = 64;      // leaf width
+constexpr int NBO = 256;    // outer panel width
+constexpr int RB = 64;      // TRSM rows per CTA in panel_kernel
+constexpr int LDR = 65;     // row buffer stride (odd -> conflict-free thread-per-row access)
+constexpr int LDT = 66;     // transposed / natural L block stride (even -> 16B-aligned rows)
+constexpr int PANEL_SMEM = ((NB + RB) * LDR + NB * LDT + 8 * 9) * 8;
+constexpr int TRSM_ROWS = 128;
+constexpr int TRSM_SMEM = (NB * LDT + NB + TRSM_ROWS * LDR) * 8;
+constexpr int LEAF_SMEM = (2 * NB * LDR) * 8;
+}  // namespace pcfg
+
+// ---------------------------------------------------------------------------------------
+// panel_kernel: factor the b x b diagonal block at (i0,i0) and solve X L11^T = A21 for the
+// rows below.  Thread-per-row, left-looking in 8-column register blocks.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(pcfg::NB + pcfg::RB) panel_kernel(double* __restrict__ A, int lda,
+                                                                    int n, int i0, int b,
+                                                                    int* __restrict__ info) {
+  using namespace pcfg;
+  extern __shared__ __align__(16) double sm[];
+  double* Rs = sm;                      // [NB+RB][LDR]
+  double* Lt = Rs + (NB + RB) * LDR;    // [NB][LDT]   Lt[k][c] = L11[c][k]
+  double* Ds = Lt + NB * LDT;           // [8][9]
+  const int tid = threadIdx.x;
+  const int nthr = NB + RB;
+  const int row_base = i0 + b + blockIdx.x * RB;
+  const int nrows = max(0, min(RB, n - row_base));
+
+  for (int idx = tid; idx < NB * NB; idx += nthr) {
+    const int r = idx >> 6, c = idx & 63;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < b && c < b) v = A[(size_t)(i0 + r) * lda + i0 + c];
+    Rs[r * LDR + c] = v;
+  }
+  for (int idx = tid; idx < RB * NB; idx += nthr) {
+    const int r = idx >> 6, c = idx & 63;
+    double v = 0.0;
+    if (r < nrows && c < b) v = A[(size_t)(row_base + r) * lda + i0 + c];
+    Rs[(NB + r) * LDR + c] = v;
+  }
+  __syncthreads();
+
+  int fail = INT_MAX;
+  double* myrow = Rs + tid * LDR;
+#pragma unroll 1
+  for (int cb = 0; cb < NB / 8; ++cb) {
+    const int c0 = cb * 8;
+    const bool active = (tid >= c0);
+    double s[8];
+    if (active) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[q] = myrow[c0 + q];
+      for (int k = 0; k < c0; ++k) {
+        const double li = myrow[k];
+        const double2* lt = reinterpret_cast<const double2*>(Lt + k * LDT + c0);
+        const double2 l01 = lt[0], l23 = lt[1], l45 = lt[2], l67 = lt[3];
+        s[0] -= li * l01.x; s[1] -= li * l01.y; s[2] -= li * l23.x; s[3] -= li * l23.y;
+        s[4] -= li * l45.x; s[5] -= li * l45.y; s[6] -= li * l67.x; s[7] -= li * l67.y;
+      }
+    }
+    if (tid >= c0 && tid < c0 + 8) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) Ds[(tid - c0) * 9 + q] = s[q];
+    }
+    __syncthreads();
+    // every thread factors the 8x8 diagonal block redundantly in registers
+    double l[8][8], inv[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+#pragma unroll
+      for (int bb = 0; bb <= a; ++bb) {
+        double v = Ds[a * 9 + bb];
+#pragma unroll
+        for (int m = 0; m < bb; ++m) v -= l[a][m] * l[bb][m];
+        if (a == bb) {
+          if (!(v > 0.0)) fail = min(fail, c0 + a);
+          l[a][a] = sqrt(v);
+          inv[a] = rsqrt(v);   // independent of the sqrt: shortens the pivot chain
+        } else {
+          l[a][bb] = v * inv[bb];
+        }
+      }
+    }
+    if (active) {
+      double x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        double v = s[q];
+#pragma unroll
+        for (int m = 0; m < q; ++m) v -= x[m] * l[q][m];
+        x[q] = v * inv[q];
+      }
+      if (tid < c0 + 8) {  // rows of the diagonal 8x8 block: exact diagonal, zero upper part
+        const int a = tid - c0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q == a) x[q] = l[q][q];
+          if (q > a) x[q] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) myrow[c0 + q] = x[q];
+      if (tid < NB) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) Lt[(c0 + q) * LDT + tid] = x[q];
+      }
+    }
+    __syncthreads();
+  }
+
+  if (blockIdx.x == 0) {
+    for (int idx = tid; idx < NB * NB; idx += nthr) {
+      const int r = idx >> 6, c = idx & 63;
+      if (r < b && c < b) A[(size_t)(i0 + r) * lda + i0 + c] = (c <= r) ? Rs[r * LDR + c] : 0.0;
+    }
+    if (tid == 0 && fail != INT_MAX && fail < b) atomicCAS(info, 0, i0 + fail + 1);
+  }
+  for (int idx = tid; idx < RB * NB; idx += nthr) {
+    const int r = idx >> 6, c = idx & 63;
+    if (r < nrows && c < b) A[(size_t)(row_base + r) * lda + i0 + c] = Rs[(NB + r) * LDR + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// trsm_rln_kernel: X <- X D^{-1} for rows [r0,r1), columns [j, j+b) of X, with
+// D = L[j:j+b, j:j+b] lower triangular (solve X D = C by back substitution over columns).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(pcfg::TRSM_ROWS) trsm_rln_kernel(const double* __restrict__ L,
+                                                                   int ldl, double* __restrict__ X,
+                                                                   int ldx, int j, int b, int r0,
+                                                                   int r1) {
+  using namespace pcfg;
+  extern __shared__ __align__(16) double sm[];
+  double* Dm = sm;                 // [NB][LDT]  natural layout D[k][c]
+  double* invd = Dm + NB * LDT;    // [NB]
+  double* Xs = invd + NB;          // [TRSM_ROWS][LDR]
+  const int tid = threadIdx.x;
+  const int row_base = r0 + blockIdx.x * TRSM_ROWS;
+  const int nrows = max(0, min(TRSM_ROWS, r1 - row_base));
+
+  for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
+    const int k = idx >> 6, c = idx & 63;
+    double v = (k == c) ? 1.0 : 0.0;
+    if (k < b && c < b) v = (c <= k) ? L[(size_t)(j + k) * ldl + j + c] : 0.0;
+    Dm[k * LDT + c] = v;
+  }
+  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
+    const int r = idx >> 6, c = idx & 63;
+    double v = 0.0;
+    if (r < nrows && c < b) v = X[(size_t)(row_base + r) * ldx + j + c];
+    Xs[r * LDR + c] = v;
+  }
+  __syncthreads();
+  if (tid < NB) invd[tid] = 1.0 / Dm[tid * LDT + tid];
+  __syncthreads();
+
+  double* myrow = Xs + tid * LDR;
+#pragma unroll 1
+  for (int cb = NB / 8 - 1; cb >= 0; --cb) {
+    const int c0 = cb * 8;
+    double s[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = myrow[c0 + q];
+    for (int k = c0 + 8; k < NB; ++k) {
+      const double xk = myrow[k];
+      const double2* dk = reinterpret_cast<const double2*>(Dm + k * LDT + c0);
+      const double2 d01 = dk[0], d23 = dk[1], d45 = dk[2], d67 = dk[3];
+      s[0] -= xk * d01.x; s[1] -= xk * d01.y; s[2] -= xk * d23.x; s[3] -= xk * d23.y;
+      s[4] -= xk * d45.x; s[5] -= xk * d45.y; s[6] -= xk * d67.x; s[7] -= xk * d67.y;
+    }
+    double x[8];
+#pragma unroll
+    for (int q = 7; q >= 0; --q) {
+      double v = s[q];
+#pragma unroll
+      for (int m = q + 1; m < 8; ++m) v -= x[m] * Dm[(c0 + m) * LDT + c0 + q];
+      x[q] = v * invd[c0 + q];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) myrow[c0 + q] = x[q];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
+    const int r = idx >> 6, c = idx & 63;
+    if (r < nrows && c < b) X[(size_t)(row_base + r) * ldx + j + c] = Xs[r * LDR + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// leaf_rev_kernel: level-2 reverse-mode of the b x b (b <= 64) diagonal block at (j,j):
+// Abar[j:j+b, j:j+b] (lower, holding Lbar) <- Abar in Murray's convention.  One CTA.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) leaf_rev_kernel(const double* __restrict__ L, int ldl,
+                                                       double* __restrict__ Ab, int ldab, int j0,
+                                                       int b) {
+  using namespace pcfg;
+  extern __shared__ __align__(16) double sm[];
+  double* D = sm;               // [NB][LDR]
+  double* X = D + NB * LDR;     // [NB][LDR]
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    double d = (r == c) ? 1.0 : 0.0, x = 0.0;
+    if (r < b && c < b && c <= r) {
+      d = L[(size_t)(j0 + r) * ldl + j0 + c];
+      x = Ab[(size_t)(j0 + r) * ldab + j0 + c];
+    }
+    D[r * LDR + c] = d;
+    X[r * LDR + c] = x;
+  }
+  __syncthreads();
+
+#pragma unroll 1
+  for (int j = b - 1; j >= 0; --j) {
+    // Phase A (each warp redundantly): dbar = (X_jj - <c, cbar>/d)/d
+    double part = 0.0;
+    for (int i = j + 1 + lane; i < b; i += 32) part += D[i * LDR + j] * X[i * LDR + j];
+    const double tsum = warp_sum(part);
+    const double rd = 1.0 / D[j * LDR + j];
+    const double dbar = (X[j * LDR + j] - tsum * rd) * rd;
+    // Phase B: rbar_k -= dbar r_k + sum_i cbar_i B_ik ; Bbar_ik -= cbar_i r_k  (cbar = X[:,j]/d)
+    {
+      const int k = tid >> 2, sub = tid & 3;
+      double acc = 0.0;
+      if (k < j)
+        for (int i = j + 1 + sub; i < b; i += 4) acc += X[i * LDR + j] * D[i * LDR + k];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (k < j && sub == 0) X[j * LDR + k] -= dbar * D[j * LDR + k] + acc * rd;
+    }
+    if (j > 0) {
+      const int cnt = (b - 1 - j) * j;
+      for (int idx = tid; idx < cnt; idx += 256) {
+        const int i = j + 1 + idx / j, k = idx % j;
+        X[i * LDR + k] -= X[i * LDR + j] * rd * D[j * LDR + k];
+      }
+    }
+    __syncthreads();
+    // Phase C: finalise column j (not read again)
+    if (tid > j && tid < b) X[tid * LDR + j] *= rd;
+    if (tid == j) X[j * LDR + j] = 0.5 * dbar;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    if (r < b && c < b && c <= r) Ab[(size_t)(j0 + r) * ldab + j0 + c] = X[r * LDR + c];
+  }
+}
+
+// ws[b x b] (ld = b) = Xl + Xl^T with Xl = tril(Ab[j:j+b, j:j+b])
+__global__ void symmetrize_block_kernel(const double* __restrict__ Ab, int ldab, int j0, int b,
+                                        double* __restrict__ ws) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r >= b || c >= b) return;
+  double v;
+  if (r == c) v = 2.0 * Ab[(size_t)(j0 + r) * ldab + j0 + c];
+  else if (c < r) v = Ab[(size_t)(j0 + r) * ldab + j0 + c];
+  else v = Ab[(size_t)(j0 + c) * ldab + j0 + r];
+  ws[(size_t)r * b + c] = v;
+}
+
+__global__ void zero_upper_kernel(double* __restrict__ A, int n, int lda) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r < n && c < n && c > r) A[(size_t)r * lda + c] = 0.0;
+}
+
+// In place: lower triangle in Murray's convention -> full symmetric gradient G.
+__global__ void finalize_sym_kernel(double* __restrict__ Ab, int n, int ld) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r >= n || c >= n || c >= r) return;
+  const double v = 0.5 * Ab[(size_t)r * ld + c];
+  Ab[(size_t)r * ld + c] = v;
+  Ab[(size_t)c * ld + r] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------------------
+static int set_smem_attrs() {
+  static bool done = false;
+  if (done) return GPINV_OK;
+  cudaError_t e;
+  e = cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pcfg::PANEL_SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(trsm_rln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pcfg::TRSM_SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(leaf_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pcfg::LEAF_SMEM);
+  if (e != cudaSuccess) {
+    set_last_error(cudaGetErrorString(e));
+    return GPINV_ERR_CUDA;
+  }
+  done = true;
+  return GPINV_OK;
+}
+
+static int pick_splitk(int M, int N, int K, bool lower) {
+  const int tm = cdiv(M, gemm_cfg::BM), tn = cdiv(N, gemm_cfg::BN);
+  const int tiles = lower ? tm * (tm + 1) / 2 : tm * tn;
+  const int ktiles = cdiv(K, gemm_cfg::BK);
+  int s = 148 / (tiles > 0 ? tiles : 1);
+  s = min(s, ktiles / 8);   // keep >= 8 k-tiles (128 columns of K) per split
+  return max(s, 1);
+}
+
+int potrf_f64(double* A, int n, int lda, int* info, cudaStream_t st) {
+  using namespace pcfg;
+  int rc = set_smem_attrs();
+  if (rc) return rc;
+  if (cudaMemsetAsync(info, 0, sizeof(int), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  for (int o = 0; o < n; o += NBO) {
+    const int w = min(NBO, n - o);
+    for (int i = o; i < o + w; i += NB) {
+      const int b = min(NB, o + w - i);
+      const int below = n - i - b;
+      panel_kernel<<<max(1, cdiv(below, RB)), NB + RB, PANEL_SMEM, st>>>(A, lda, n, i, b, info);
+      GPINV_CHECK_LAUNCH();
+      if (i + b < o + w) {
+        double* P = A + (size_t)(i + b) * lda + i;
+        rc = gemm_simple(LK, LK, n - (i + b), o + w - (i + b), b, -1.0, P, lda, P, lda, 1.0,
+                         A + (size_t)(i + b) * lda + (i + b), lda, false, 0, 1, st);
+        if (rc) return rc;
+      }
+    }
+    if (o + w < n) {
+      double* P = A + (size_t)(o + w) * lda + o;
+      rc = gemm_simple(LK, LK, n - o - w, n - o - w, w, -1.0, P, lda, P, lda, 1.0,
+                       A + (size_t)(o + w) * lda + (o + w), lda, true, 0, 1, st);
+      if (rc) return rc;
+    }
+  }
+  dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n, 8));
+  zero_upper_kernel<<<grd, blk, 0, st>>>(A, n, lda);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
+// X[r0:r1, j:k] <- X[r0:r1, j:k] D^{-1}, D = L[j:k, j:k]; blocked over 64-wide leaves.
+static int trsm_rln_blocked(const double* L, int ldl, double* X, int ldx, int j, int k, int r0,
+                            int r1, cudaStream_t st) {
+  using namespace pcfg;
+  if (r1 <= r0) return GPINV_OK;
+  int jb = k;
+  while (jb > j) {
+    const int ja = max(j, jb - NB);
+    trsm_rln_kernel<<<cdiv(r1 - r0, TRSM_ROWS), TRSM_ROWS, TRSM_SMEM, st>>>(L, ldl, X, ldx, ja,
+                                                                            jb - ja, r0, r1);
+    GPINV_CHECK_LAUNCH();
+    if (ja > j) {
+      int rc = gemm_simple(LK, LMN, r1 - r0, ja - j, jb - ja, -1.0, X + (size_t)r0 * ldx + ja, ldx,
+                           L + (size_t)ja * ldl + j, ldl, 1.0, X + (size_t)r0 * ldx + j, ldx, false,
+                           0, 1, st);
+      if (rc) return rc;
+    }
+    jb = ja;
+  }
+  return GPINV_OK;
+}
+
+// Reverse sweep restricted to the diagonal block [s,e) of (L, Ab).
+static int potrf_bwd_range(const double* L, int ldl, double* Ab, int ldab, int s, int e, int nb,
+                           bool two_level, double* ws, cudaStream_t st) {
+  using namespace pcfg;
+  int rc;
+  int k = e;
+  while (k > s) {
+    const int j = max(s, k - nb);
+    const int bw = k - j;
+    if (k < e) {
+      rc = trsm_rln_blocked(L, ldl, Ab, ldab, j, k, k, e, st);   // Cbar <- Cbar D^{-1}
+      if (rc) return rc;
+      const double* Cb = Ab + (size_t)k * ldab + j;
+      if (j > s) {  // Bbar -= Cbar R
+        rc = gemm_simple(LK, LMN, e - k, j - s, bw, -1.0, Cb, ldab, L + (size_t)j * ldl + s, ldl,
+                         1.0, Ab + (size_t)k * ldab + s, ldab, false, 0, 1, st);
+        if (rc) return rc;
+      }
+      {  // Dbar -= tril(Cbar^T C)
+        const int sk = pick_splitk(bw, bw, e - k, true);
+        rc = gemm_simple(LMN, LMN, bw, bw, e - k, -1.0, Cb, ldab, L + (size_t)k * ldl + j, ldl, 1.0,
+                         Ab + (size_t)j * ldab + j, ldab, true, 0, sk, st);
+        if (rc) return rc;
+      }
+    }
+    if (two_level) {
+      rc = potrf_bwd_range(L, ldl, Ab, ldab, j, k, NB, false, ws, st);
+      if (rc) return rc;
+    } else {
+      leaf_rev_kernel<<<1, 256, LEAF_SMEM, st>>>(L, ldl, Ab, ldab, j, bw);
+      GPINV_CHECK_LAUNCH();
+    }
+    if (j > s) {
+      if (k < e) {  // Rbar -= Cbar^T B
+        const int sk = pick_splitk(bw, j - s, e - k, false);
+        rc = gemm_simple(LMN, LMN, bw, j - s, e - k, -1.0, Ab + (size_t)k * ldab + j, ldab,
+                         L + (size_t)k * ldl + s, ldl, 1.0, Ab + (size_t)j * ldab + s, ldab, false,
+                         0, sk, st);
+        if (rc) return rc;
+      }
+      // Rbar -= (Dbar + Dbar^T) R
+      dim3 blk(32, 8), grd(cdiv(bw, 32), cdiv(bw, 8));
+      symmetrize_block_kernel<<<grd, blk, 0, st>>>(Ab, ldab, j, bw, ws);
+      GPINV_CHECK_LAUNCH();
+      rc = gemm_simple(LK, LMN, bw, j - s, bw, -1.0, ws, bw, L + (size_t)j * ldl + s, ldl, 1.0,
+                       Ab + (size_t)j * ldab + s, ldab, false, 0, 1, st);
+      if (rc) return rc;
+    }
+    k = j;
+  }
+  return GPINV_OK;
+}
+
+size_t potrf_bwd_ws_bytes(int n) {
+  (void)n;
+  // one outer-level and one inner-level symmetrised block
+  return (size_t)(pcfg::NBO * pcfg::NBO + pcfg::NB * pcfg::NB) * sizeof(double);
+}
+
+// Ab holds Lbar (lower) on entry; on exit the full symmetric gradient dF/dA.
+int potrf_bwd_f64(const double* L, int ldl, double* Ab, int ldab, int n, double* ws,
+                  cudaStream_t st) {
+  using namespace pcfg;
+  int rc = set_smem_attrs();
+  if (rc) return rc;
+  // The inner level needs its own symmetrise buffer: it runs between the outer level's
+  // symmetrise and its consumer only across iterations, never inside one, but keep them apart.
+  double* ws_outer = ws;
+  double* ws_inner = ws + (size_t)NBO * NBO;
+  // outer level uses ws_outer; potrf_bwd_range passes `ws` down, so wrap manually:
+  int k = n;
+  while (k > 0) {
+    const int j = max(0, k - NBO);
+    const int bw = k - j;
+    if (k < n) {
+      rc = trsm_rln_blocked(L, ldl, Ab, ldab, j, k, k, n, st);
+      if (rc) return rc;
+      const double* Cb = Ab + (size_t)k * ldab + j;
+      if (j > 0) {
+        rc = gemm_simple(LK, LMN, n - k, j, bw, -1.0, Cb, ldab, L + (size_t)j * ldl, ldl, 1.0,
+                         Ab + (size_t)k * ldab, ldab, false, 0, 1, st);
+        if (rc) return rc;
+      }
+      const int sk = pick_splitk(bw, bw, n - k, true);
+      rc = gemm_simple(LMN, LMN, bw, bw, n - k, -1.0, Cb, ldab, L + (size_t)k * ldl + j, ldl, 1.0,
+                       Ab + (size_t)j * ldab + j, ldab, true, 0, sk, st);
+      if (rc) return rc;
+    }
+    rc = potrf_bwd_range(L, ldl, Ab, ldab, j, k, NB, false, ws_inner, st);
+    if (rc) return rc;
+    if (j > 0) {
+      if (k < n) {
+        const int sk = pick_splitk(bw, j, n - k, false);
+        rc = gemm_simple(LMN, LMN, bw, j, n - k, -1.0, Ab + (size_t)k * ldab + j, ldab,
+                         L + (size_t)k * ldl, ldl, 1.0, Ab + (size_t)j * ldab, ldab, false, 0, sk,
+                         st);
+        if (rc) return rc;
+      }
+      dim3 blk(32, 8), grd(cdiv(bw, 32), cdiv(bw, 8));
+      symmetrize_block_kernel<<<grd, blk, 0, st>>>(Ab, ldab, j, bw, ws_outer);
+      GPINV_CHECK_LAUNCH();
+      rc = gemm_simple(LK, LMN, bw, j, bw, -1.0, ws_outer, bw, L + (size_t)j * ldl, ldl, 1.0,
+                       Ab + (size_t)j * ldab, ldab, false, 0, 1, st);
+      if (rc) return rc;
+    }
+    k = j;
+  }
+  dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n, 8));
+  finalize_sym_kernel<<<grd, blk, 0, st>>>(Ab, n, ldab);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
+// Solve X L^T = B in place (B is m x n row-major, L n x n lower): forward substitution over
+// columns, i.e. row-wise "L x = b" for every row of B.  Used by the whitened conditional
+// (GPinv/conditionals.py:44: A = Lm^{-1} Kmn, applied here to Kmn^T).
+__global__ void __launch_bounds__(pcfg::TRSM_ROWS) trsm_rlt_kernel(const double* __restrict__ L,
+                                                                   int ldl, double* __restrict__ X,
+                                                                   int ldx, int j, int b, int r0,
+                                                                   int r1) {
+  using namespace pcfg;
+  extern __shared__ __align__(16) double sm[];
+  double* Lt = sm;                 // [NB][LDT]  Lt[k][c] = D[c][k]
+  double* invd = Lt + NB * LDT;    // [NB]
+  double* Xs = invd + NB;          // [TRSM_ROWS][LDR]
+  const int tid = threadIdx.x;
+  const int row_base = r0 + blockIdx.x * TRSM_ROWS;
+  const int nrows = max(0, min(TRSM_ROWS, r1 - row_base));
+  for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
+    const int c = idx >> 6, k = idx & 63;   // read D[c][k] coalesced over k
+    double v = (k == c) ? 1.0 : 0.0;
+    if (k < b && c < b) v = (k <= c) ? L[(size_t)(j + c) * ldl + j + k] : 0.0;
+    Lt[k * LDT + c] = v;
+  }
+  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
+    const int r = idx >> 6, c = idx & 63;
+    double v = 0.0;
+    if (r < nrows && c < b) v = X[(size_t)(row_base + r) * ldx + j + c];
+    Xs[r * LDR + c] = v;
+  }
+  __syncthreads();
+  if (tid < NB) invd[tid] = 1.0 / Lt[tid * LDT + tid];
+  __syncthreads();
+  double* myrow = Xs + tid * LDR;
+#pragma unroll 1
+  for (int cb = 0; cb < NB / 8; ++cb) {
+    const int c0 = cb * 8;
+    double s[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = myrow[c0 + q];
+    for (int k = 0; k < c0; ++k) {
+      const double xk = myrow[k];
+      const double2* lt = reinterpret_cast<const double2*>(Lt + k * LDT + c0);
+      const double2 l01 = lt[0], l23 = lt[1], l45 = lt[2], l67 = lt[3];
+      s[0] -= xk * l01.x; s[1] -= xk * l01.y; s[2] -= xk * l23.x; s[3] -= xk * l23.y;
+      s[4] -= xk * l45.x; s[5] -= xk * l45.y; s[6] -= xk * l67.x; s[7] -= xk * l67.y;
+    }
+    double x[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      double v = s[q];
+#pragma unroll
+      for (int m = 0; m < q; ++m) v -= x[m] * Lt[(c0 + m) * LDT + c0 + q];
+      x[q] = v * invd[c0 + q];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) myrow[c0 + q] = x[q];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
+    const int r = idx >> 6, c = idx & 63;
+    if (r < nrows && c < b) X[(size_t)(row_base + r) * ldx + j + c] = Xs[r * LDR + c];
+  }
+}
+
+int trsm_rlt_f64(const double* L, int ldl, double* X, int ldx, int m, int n, cudaStream_t st) {
+  using namespace pcfg;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(trsm_rlt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TRSM_SMEM) != cudaSuccess)
+      return GPINV_ERR_CUDA;
+    attr = true;
+  }
+  if (m <= 0) return GPINV_OK;
+  for (int j = 0; j < n; j += NB) {
+    const int b = min(NB, n - j);
+    trsm_rlt_kernel<<<cdiv(m, TRSM_ROWS), TRSM_ROWS, TRSM_SMEM, st>>>(L, ldl, X, ldx, j, b, 0, m);
+    GPINV_CHECK_LAUNCH();
+    if (j + b < n) {  // X[:, j+b:] -= X[:, j:j+b] L[j+b:, j:j+b]^T
+      int rc = gemm_simple(LK, LK, m, n - j - b, b, -1.0, X + j, ldx, L + (size_t)(j + b) * ldl + j,
+                           ldl, 1.0, X + j + b, ldx, false, 0, 1, st);
+      if (rc) return rc;
+    }
+  }
+  return GPINV_OK;
+}
+
+}  // namespace gpinv

@@ -1,0 +1,356 @@
+"""PyTorch custom ops (``torch.ops.gpinv.*``) over the C ABI of ``libgpinv_sm100.so``.
+
+Each op is a thin wrapper: it allocates outputs with torch (device memory and streams are
+torch's job), then calls one ``gpinv_*_f64`` entry point on the current CUDA stream.  The
+backward of every op is hand-written CUDA too (registered with ``register_autograd``) — the
+reference obtains it from ``tf.gradients`` (pattern at GPinv/model.py:35-37).
+
+CUDA only.  There is no CPU implementation: calling an op with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _capi
+
+MODE = {"rbf": 0, "rbf_csym": 1, "rbf_casym": 2}
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t: Tensor, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("gpinv_b200 ops are CUDA-only (no CPU fallback): %s is on %s" % (name, t.device))
+    if t.dtype != torch.float64:
+        raise RuntimeError("gpinv_b200 ops are fp64-only: %s is %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _ws(nbytes: int, like: Tensor) -> Tensor:
+    return torch.empty(max(int(nbytes) // 8 + 2, 2), dtype=torch.float64, device=like.device)
+
+
+# --------------------------------------------------------------------------------------
+# T1-T3 kernel core
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("gpinv::kcore", mutates_args=(), device_types="cuda")
+def kcore(X: Tensor, X2: Optional[Tensor], ls: Tensor, mode: int, jitter: float) -> Tensor:
+    """core(X, X2) [n,n2] (+ jitter on the diagonal when X2 is None).
+    GPinv/kernels.py:57-58,105-107,115-120,140-145."""
+    X = _chk(X, "X")
+    ls = _chk(ls, "ls").reshape(-1)
+    n, D = X.shape
+    n2 = n
+    if X2 is not None:
+        X2 = _chk(X2, "X2")
+        n2 = X2.shape[0]
+    ard = 1 if ls.numel() > 1 else 0
+    K = torch.empty((n, n2), dtype=torch.float64, device=X.device)
+    L = _capi.lib()
+    ws = _ws(L.gpinv_kbuild_ws_bytes(n, n2, D), X)
+    rc = L.gpinv_kbuild_f64(_p(X), _p(X2), n, n2, D, D, D, _p(ls), ard, mode, float(jitter),
+                            _p(K), n2, _p(ws), _st())
+    _capi.check(rc, "kbuild")
+    return K
+
+
+@torch.library.custom_op("gpinv::kcore_bwd", mutates_args=(), device_types="cuda")
+def kcore_bwd(X: Tensor, X2: Optional[Tensor], ls: Tensor, mode: int, Kbar: Tensor) -> Tensor:
+    X = _chk(X, "X")
+    ls = _chk(ls, "ls").reshape(-1)
+    Kbar = _chk(Kbar, "Kbar")
+    n, D = X.shape
+    n2 = n
+    if X2 is not None:
+        X2 = _chk(X2, "X2")
+        n2 = X2.shape[0]
+    ard = 1 if ls.numel() > 1 else 0
+    out = torch.empty_like(ls)
+    L = _capi.lib()
+    ws = _ws(L.gpinv_kbuild_ws_bytes(n, n2, D), X)
+    rc = L.gpinv_kbuild_bwd_f64(_p(X), _p(X2), n, n2, D, D, D, _p(ls), ard, mode, _p(Kbar), n2,
+                                _p(out), _p(ws), _st())
+    _capi.check(rc, "kbuild_bwd")
+    return out
+
+
+def _kcore_setup(ctx, inputs, output):
+    X, X2, ls, mode, jitter = inputs
+    ctx.save_for_backward(X, X2, ls) if X2 is not None else ctx.save_for_backward(X, ls)
+    ctx.has_x2 = X2 is not None
+    ctx.mode = mode
+    ctx.ls_shape = ls.shape
+
+
+def _kcore_backward(ctx, Kbar):
+    if ctx.has_x2:
+        X, X2, ls = ctx.saved_tensors
+    else:
+        (X, ls), X2 = ctx.saved_tensors, None
+    g = kcore_bwd(X, X2, ls, ctx.mode, Kbar.contiguous())
+    return None, None, g.reshape(ctx.ls_shape), None, None
+
+
+kcore.register_autograd(_kcore_backward, setup_context=_kcore_setup)
+
+
+# --------------------------------------------------------------------------------------
+# T4 Cholesky
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("gpinv::potrf", mutates_args=(), device_types="cuda")
+def potrf(K: Tensor) -> Tuple[Tensor, Tensor]:
+    """(L, info): lower Cholesky factor with zeroed strict upper triangle; info int32[1] is the
+    1-based first failing pivot (0 = success).  GPinv/kernels.py:59."""
+    K = _chk(K, "K")
+    n = K.shape[0]
+    Lm = K.clone()
+    info = torch.zeros(1, dtype=torch.int32, device=K.device)
+    rc = _capi.lib().gpinv_potrf_f64(_p(Lm), n, n, _p(info), _st())
+    _capi.check(rc, "potrf")
+    return Lm, info
+
+
+@torch.library.custom_op("gpinv::potrf_bwd", mutates_args=(), device_types="cuda")
+def potrf_bwd(L: Tensor, Lbar: Tensor) -> Tensor:
+    """Symmetric dObj/dK from dObj/dL (blocked reverse sweep)."""
+    L = _chk(L, "L")
+    Ab = _chk(Lbar, "Lbar").clone()
+    n = L.shape[0]
+    lib = _capi.lib()
+    ws = _ws(lib.gpinv_potrf_bwd_ws_bytes(n), L)
+    rc = lib.gpinv_potrf_bwd_f64(_p(L), n, _p(Ab), n, n, _p(ws), _st())
+    _capi.check(rc, "potrf_bwd")
+    return Ab
+
+
+def _potrf_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[0])
+
+
+def _potrf_backward(ctx, Lbar, _info_bar):
+    (L,) = ctx.saved_tensors
+    return potrf_bwd(L, Lbar.contiguous())
+
+
+potrf.register_autograd(_potrf_backward, setup_context=_potrf_setup)
+
+
+@torch.library.custom_op("gpinv::trsm_rlt", mutates_args=(), device_types="cuda")
+def trsm_rlt(L: Tensor, B: Tensor) -> Tensor:
+    """X = B L^{-T} (B is [m,n]); i.e. every row x solves L x = b.  GPinv/conditionals.py:44."""
+    L = _chk(L, "L")
+    X = _chk(B, "B").clone()
+    m, n = X.shape
+    rc = _capi.lib().gpinv_trsm_rlt_f64(_p(L), n, _p(X), n, m, n, _st())
+    _capi.check(rc, "trsm_rlt")
+    return X
+
+
+@torch.library.custom_op("gpinv::gemm", mutates_args=(), device_types="cuda")
+def gemm(A: Tensor, B: Tensor, transa: bool, transb: bool, lower: bool) -> Tensor:
+    """op(A) @ op(B) on the DMMA kernel (used by the prediction path, GPinv/conditionals.py)."""
+    A = _chk(A, "A")
+    B = _chk(B, "B")
+    m, k = (A.shape[1], A.shape[0]) if transa else (A.shape[0], A.shape[1])
+    n = B.shape[0] if transb else B.shape[1]
+    Cm = torch.zeros((m, n), dtype=torch.float64, device=A.device)
+    rc = _capi.lib().gpinv_gemm_f64(int(transa), int(transb), m, n, k, 1.0, _p(A), A.shape[1],
+                                    _p(B), B.shape[1], 0.0, _p(Cm), n, int(lower), _st())
+    _capi.check(rc, "gemm")
+    return Cm
+
+
+# --------------------------------------------------------------------------------------
+# T7 tril(q_sqrt): [n,n,R] -> [R,n,n]
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("gpinv::tril_unpack", mutates_args=(), device_types="cuda")
+def tril_unpack(q_sqrt: Tensor) -> Tensor:
+    q = _chk(q_sqrt, "q_sqrt")
+    n, _, R = q.shape
+    out = torch.empty((R, n, n), dtype=torch.float64, device=q.device)
+    _capi.check(_capi.lib().gpinv_tril_unpack_f64(_p(q), _p(out), n, R, _st()), "tril_unpack")
+    return out
+
+
+@torch.library.custom_op("gpinv::tril_pack", mutates_args=(), device_types="cuda")
+def tril_pack(Qbar: Tensor) -> Tensor:
+    q = _chk(Qbar, "Qbar")
+    R, n, _ = q.shape
+    out = torch.empty((n, n, R), dtype=torch.float64, device=q.device)
+    _capi.check(_capi.lib().gpinv_tril_pack_f64(_p(q), _p(out), n, R, _st()), "tril_pack")
+    return out
+
+
+tril_unpack.register_autograd(lambda ctx, g: tril_pack(g.contiguous()), setup_context=lambda ctx, inputs, output: None)
+
+
+# --------------------------------------------------------------------------------------
+# T8-T13 sampling
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("gpinv::stvgp_sample", mutates_args=(), device_types="cuda")
+def stvgp_sample(Lc: Tensor, sqrt_v: Tensor, Q: Tensor, q_mu: Tensor, mean: Tensor, E: Tensor,
+                 q_diag: bool, want_exp: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """(F [R,S,n], expF [R,S,n] or empty, KL [1], U [R,S,n]).  GPinv/stvgp.py:144-185.
+    Lc [n,n] lower core factor, sqrt_v [R], Q [R,n,n] lower (or [R,n] if q_diag), q_mu [R,n],
+    mean [R,n], E [R,S,n]."""
+    Lc = _chk(Lc, "Lc"); sqrt_v = _chk(sqrt_v, "sqrt_v"); Q = _chk(Q, "Q")
+    q_mu = _chk(q_mu, "q_mu"); mean = _chk(mean, "mean"); E = _chk(E, "E")
+    R, S, n = E.shape
+    U = torch.empty_like(E)
+    F = torch.empty_like(E)
+    expF = torch.empty_like(E) if want_exp else torch.empty(0, dtype=torch.float64, device=E.device)
+    kl = torch.empty(4, dtype=torch.float64, device=E.device)
+    rc = _capi.lib().gpinv_sample_fwd_f64(_p(Lc), n, _p(sqrt_v), _p(Q), int(q_diag), _p(q_mu),
+                                          _p(mean), _p(E), n, S, R, _p(U), _p(F),
+                                          _p(expF) if want_exp else None, _p(kl), _st())
+    _capi.check(rc, "sample_fwd")
+    return F, expF, kl[:1].clone(), U
+
+
+@torch.library.custom_op("gpinv::stvgp_sample_bwd", mutates_args=(), device_types="cuda")
+def stvgp_sample_bwd(Lc: Tensor, sqrt_v: Tensor, Q: Tensor, E: Tensor, U: Tensor, Fbar: Tensor,
+                     klbar: Optional[Tensor], q_diag: bool) -> List[Tensor]:
+    """[Lc_bar, sqrt_v_bar, Qbar, qmu_bar, mean_bar]."""
+    Lc = _chk(Lc, "Lc"); sqrt_v = _chk(sqrt_v, "sqrt_v"); Q = _chk(Q, "Q")
+    E = _chk(E, "E"); U = _chk(U, "U"); Fbar = _chk(Fbar, "Fbar")
+    if klbar is not None:
+        klbar = _chk(klbar, "klbar")
+    R, S, n = E.shape
+    dev = E.device
+    Ubar = torch.empty_like(E)
+    qmu_bar = torch.empty((R, n), dtype=torch.float64, device=dev)
+    Qbar = torch.empty_like(Q)
+    Lc_bar = torch.empty((n, n), dtype=torch.float64, device=dev)
+    svdot = torch.empty(R, dtype=torch.float64, device=dev)
+    mean_bar = torch.empty((R, n), dtype=torch.float64, device=dev)
+    rc = _capi.lib().gpinv_sample_bwd_f64(_p(Lc), n, _p(sqrt_v), _p(Q), int(q_diag), _p(E), _p(U),
+                                          _p(Fbar), _p(klbar), n, S, R, _p(Ubar), _p(qmu_bar),
+                                          _p(Qbar), _p(Lc_bar), n, _p(svdot), _p(mean_bar), _st())
+    _capi.check(rc, "sample_bwd")
+    return [Lc_bar, svdot / sqrt_v, Qbar, qmu_bar, mean_bar]
+
+
+def _sample_setup(ctx, inputs, output):
+    Lc, sqrt_v, Q, q_mu, mean, E, q_diag, want_exp = inputs
+    F, expF, kl, U = output
+    ctx.save_for_backward(Lc, sqrt_v, Q, E, U, expF)
+    ctx.q_diag = q_diag
+    ctx.want_exp = want_exp
+
+
+def _sample_backward(ctx, Fbar, expFbar, klbar, Ubar_unused):
+    Lc, sqrt_v, Q, E, U, expF = ctx.saved_tensors
+    if Fbar is None:
+        Fbar = torch.zeros_like(E)
+    if ctx.want_exp and expFbar is not None:
+        Fbar = Fbar + expFbar * expF
+    Lc_bar, sv_bar, Qbar, qmu_bar, mean_bar = stvgp_sample_bwd(
+        Lc, sqrt_v, Q, E, U, Fbar.contiguous(), None if klbar is None else klbar.contiguous(),
+        ctx.q_diag)
+    # Qbar's strict upper triangle is unspecified; tril_unpack's backward masks it.  For the
+    # q_diag layout Qbar is exact.
+    return Lc_bar, sv_bar, Qbar, qmu_bar, mean_bar, None, None, None
+
+
+stvgp_sample.register_autograd(_sample_backward, setup_context=_sample_setup)
+
+
+# --------------------------------------------------------------------------------------
+# T14 Gaussian likelihood on latent samples
+# --------------------------------------------------------------------------------------
+LOG2PI = 1.8378770664093453
+
+
+@torch.library.custom_op("gpinv::gauss_sumsq", mutates_args=(), device_types="cuda")
+def gauss_sumsq(F: Tensor, Y: Tensor) -> Tensor:
+    """sum_{r,s,i} (F[r,s,i] - Y[i,r])^2 -> [1]."""
+    F = _chk(F, "F"); Y = _chk(Y, "Y")
+    R, S, n = F.shape
+    out = torch.empty(1, dtype=torch.float64, device=F.device)
+    _capi.check(_capi.lib().gpinv_gauss_sumsq_f64(_p(F), _p(Y), n, S, R, _p(out), _st()), "gauss_sumsq")
+    return out
+
+
+@torch.library.custom_op("gpinv::gauss_resid_scaled", mutates_args=(), device_types="cuda")
+def gauss_resid_scaled(F: Tensor, Y: Tensor, coef: Tensor) -> Tensor:
+    """coef * (Y - F) -> [R,S,n]."""
+    F = _chk(F, "F"); Y = _chk(Y, "Y"); coef = _chk(coef, "coef")
+    R, S, n = F.shape
+    out = torch.empty_like(F)
+    _capi.check(_capi.lib().gpinv_gauss_bwd_f64(_p(F), _p(Y), n, S, R, _p(coef), _p(out), _st()), "gauss_bwd")
+    return out
+
+
+def _gss_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _gss_backward(ctx, g):
+    F, Y = ctx.saved_tensors
+    # d/dF sum (F-Y)^2 = 2 (F - Y) = -2 (Y - F)
+    return gauss_resid_scaled(F, Y, (-2.0 * g).reshape(1).contiguous()), None
+
+
+gauss_sumsq.register_autograd(_gss_backward, setup_context=_gss_setup)
+
+
+# --------------------------------------------------------------------------------------
+# T15 Abel transform + residual
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("gpinv::abel_resid", mutates_args=(), device_types="cuda")
+def abel_resid(F: Tensor, expF: Tensor, A: Tensor, Y: Tensor) -> Tuple[Tensor, Tensor]:
+    """(sumsq [1], Rs [S,M]) with Rs = 1 y^T - exp(F) A^T.  F, expF [S,n]; A [M,n]; Y [M].
+    `expF` must equal exp(F) (it is the second output of stvgp_sample); gradients flow to F."""
+    expF = _chk(expF, "expF"); A = _chk(A, "A"); Y = _chk(Y, "Y")
+    S, n = expF.shape
+    M = A.shape[0]
+    Rs = torch.empty((S, M), dtype=torch.float64, device=expF.device)
+    ss = torch.empty(1, dtype=torch.float64, device=expF.device)
+    rc = _capi.lib().gpinv_abel_fwd_f64(_p(expF), _p(A), n, _p(Y), n, M, S, _p(Rs), _p(ss), _st())
+    _capi.check(rc, "abel_fwd")
+    return ss, Rs
+
+
+@torch.library.custom_op("gpinv::abel_bwd", mutates_args=(), device_types="cuda")
+def abel_bwd(Rs: Tensor, A: Tensor, expF: Tensor, coef: Tensor) -> Tensor:
+    """coef * expF o (Rs A) -> [S,n]."""
+    Rs = _chk(Rs, "Rs"); A = _chk(A, "A"); expF = _chk(expF, "expF"); coef = _chk(coef, "coef")
+    S, M = Rs.shape
+    n = A.shape[1]
+    out = torch.empty((S, n), dtype=torch.float64, device=Rs.device)
+    rc = _capi.lib().gpinv_abel_bwd_f64(_p(Rs), _p(A), n, _p(expF), _p(coef), n, M, S, _p(out), _st())
+    _capi.check(rc, "abel_bwd")
+    return out
+
+
+def _abel_setup(ctx, inputs, output):
+    F, expF, A, Y = inputs
+    ctx.save_for_backward(output[1], A, expF)
+
+
+def _abel_backward(ctx, g_ss, g_rs_unused):
+    Rs, A, expF = ctx.saved_tensors
+    # d sumsq / dF[s,j] = 2 sum_m Rs[s,m] * (-A[m,j] expF[s,j])
+    Fbar = abel_bwd(Rs, A, expF, (-2.0 * g_ss).reshape(1).contiguous())
+    return Fbar, None, None, None
+
+
+abel_resid.register_autograd(_abel_backward, setup_context=_abel_setup)
+
+
+@torch.library.custom_op("gpinv::sumsq", mutates_args=(), device_types="cuda")
+def sumsq(x: Tensor) -> Tensor:
+    x = _chk(x, "x")
+    out = torch.empty(1, dtype=torch.float64, device=x.device)
+    _capi.check(_capi.lib().gpinv_sumsq_f64(_p(x), x.numel(), _p(out), _st()), "sumsq")
+    return out

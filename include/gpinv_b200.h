@@ -1,0 +1,108 @@
+/* gpinv_b200 — C ABI of the B200 (sm_100a) StVGP / GPMC hot path.
+ *
+ * The reference (fujii-team/GPinv) has no FFI: its hot path is a TensorFlow graph built in
+ * Python.  Each entry point below replaces the group of TF ops emitted by the cited reference
+ * lines, and is what a ctypes binding on the reference side would load.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp64 (or int32 for `info`) unless stated otherwise;
+ *    the library never allocates or frees device memory — workspaces are passed in;
+ *  - matrices are row-major with an explicit leading dimension (elements);
+ *  - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no synchronisation);
+ *  - return value: 0 ok, <0 argument / CUDA error (message from gpinv_last_error());
+ *    numerical failure of the Cholesky is reported LAPACK-style in the device int `info`
+ *    (first failing pivot, 1-based), like tf.cholesky's InvalidArgumentError;
+ *  - sample matrices are stored sample-major [R][S][n] (the reference's eps layout
+ *    [R,N,n,1], GPinv/stvgp.py:164).
+ */
+#ifndef GPINV_B200_H
+#define GPINV_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPINV_MODE_RBF 0   /* GPinv/kernels.py:105-107 */
+#define GPINV_MODE_CSYM 1  /* GPinv/kernels.py:115-120 */
+#define GPINV_MODE_CASYM 2 /* GPinv/kernels.py:140-145 */
+
+int gpinv_version(void);
+const char* gpinv_last_error(void);
+
+/* --- T1-T3: kernel core matrix.  Replaces Kern._Kcore + jitter (GPinv/kernels.py:57-58,
+ * 105-107,115-120,140-145; GPflow Stationary.square_dist).  X [n,D], X2 [n2,D] or NULL
+ * (then K is n x n and `jitter` is added to its diagonal); ls device [D] (ard) or [1]. */
+size_t gpinv_kbuild_ws_bytes(int n, int n2, int D);
+int gpinv_kbuild_f64(const double* X, const double* X2, int n, int n2, int D, int ldx, int ldx2,
+                     const double* ls, int ard, int mode, double jitter, double* K, int ldk,
+                     void* ws, void* stream);
+/* reverse: ls_bar[D or 1] = sum_ij Kbar_ij dcore_ij/dls (replaces tf.gradients through _Kcore) */
+int gpinv_kbuild_bwd_f64(const double* X, const double* X2, int n, int n2, int D, int ldx,
+                         int ldx2, const double* ls, int ard, int mode, const double* Kbar,
+                         int ldkb, double* ls_bar, void* ws, void* stream);
+
+/* --- T4: Cholesky, in place, lower, strict upper zeroed.  Replaces tf.cholesky at
+ * GPinv/kernels.py:59, GPinv/kronecker.py:54,57. */
+int gpinv_potrf_f64(double* A, int n, int lda, int* info, void* stream);
+/* reverse (replaces TF's CholeskyGrad): Abar holds Lbar (lower) on entry, the full symmetric
+ * dObj/dA on exit. */
+size_t gpinv_potrf_bwd_ws_bytes(int n);
+int gpinv_potrf_bwd_f64(const double* L, int ldl, double* Abar, int ldab, int n, void* ws,
+                        void* stream);
+/* --- T22: X <- X L^{-T} (row-wise forward substitution; X is m x n).  Replaces
+ * tf.batch_matrix_triangular_solve at GPinv/conditionals.py:44 (applied to Kmn^T). */
+int gpinv_trsm_rlt_f64(const double* L, int ldl, double* X, int ldx, int m, int n, void* stream);
+
+/* --- generic DMMA GEMM: C = alpha op(A) op(B) + beta C.  transa/transb as in row-major BLAS
+ * ('N' = 0, 'T' = 1).  lower != 0: only the lower triangle of a square C is computed. */
+int gpinv_gemm_f64(int transa, int transb, int m, int n, int k, double alpha, const double* A,
+                   int lda, const double* B, int ldb, double beta, double* C, int ldc, int lower,
+                   void* stream);
+
+/* --- T7: tril(q_sqrt) with the reference's [n,n,R] -> [R,n,n] transpose
+ * (GPinv/stvgp.py:156-157) and its reverse. */
+int gpinv_tril_unpack_f64(const double* q_sqrt_nnR, double* Q_Rnn, int n, int R, void* stream);
+int gpinv_tril_pack_f64(const double* Qbar_Rnn, double* out_nnR, int n, int R, void* stream);
+
+/* --- T8-T13: u = q_mu + tril(q_sqrt) eps, KL_MC, f = sqrt(v) Lc u + mean
+ * (GPinv/stvgp.py:144-185 with Kern.Cholesky's sqrt(variance) scaling, GPinv/kernels.py:60-63,
+ * folded in as a scalar).  Q: [R,n,n] lower (q_diag=0) or [R,n] (q_diag=1).
+ * Outputs U [R,S,n]; F and/or expF [R,S,n] (either may be NULL, not both);
+ * kl_out device [4] = {KL, sum eps^2, sum u^2, sum log Q_ii^2}. */
+int gpinv_sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q,
+                         int q_diag, const double* q_mu, const double* mean, const double* E,
+                         int n, int S, int R, double* U, double* F, double* expF, double* kl_out,
+                         void* stream);
+/* reverse.  Fbar [R,S,n] = dObj/dF, klbar device scalar dObj/dKL (NULL = 0).
+ * Outputs: Ubar [R,S,n]; qmu_bar [R,n]; Qbar [R,n,n] lower (or [R,n]); Lc_bar [n,n] lower
+ * (summed over r); svdot [R] = sv_r <tril(Fbar_r^T U_r), Lc>; mean_bar [R,n]. */
+int gpinv_sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q,
+                         int q_diag, const double* E, const double* U, const double* Fbar,
+                         const double* klbar, int n, int S, int R, double* Ubar, double* qmu_bar,
+                         double* Qbar, double* Lc_bar, int ldlb, double* svdot, double* mean_bar,
+                         void* stream);
+
+/* --- T14: Gaussian likelihood (GPinv/likelihoods.py:70-76): sum (F - Y)^2 over [R,S,n] with
+ * Y [n,R]; reverse Fbar = coef (Y - F), coef a device scalar. */
+int gpinv_gauss_sumsq_f64(const double* F, const double* Y, int n, int S, int R, double* out,
+                          void* stream);
+int gpinv_gauss_bwd_f64(const double* F, const double* Y, int n, int S, int R, const double* coef,
+                        double* Fbar, void* stream);
+
+/* --- T15: Abel transform + Gaussian residual (notebooks/Abel_inversion.ipynb:274-283).
+ * Rs [S,M] = 1 y^T - expF [S,n] A[M,n]^T, *sumsq = sum Rs^2;
+ * reverse Fbar [S,n] = coef expF o (Rs A), coef device scalar (= dObj/dlik / variance). */
+int gpinv_abel_fwd_f64(const double* expF, const double* A, int lda, const double* Y, int n, int M,
+                       int S, double* Rs, double* sumsq, void* stream);
+int gpinv_abel_bwd_f64(const double* Rs, const double* A, int lda, const double* expF,
+                       const double* coef, int n, int M, int S, double* Fbar, void* stream);
+
+/* --- reductions used by T8/T11/T17 */
+int gpinv_sumsq_f64(const double* x, size_t count, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPINV_B200_H */

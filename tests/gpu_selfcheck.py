@@ -1,0 +1,191 @@
+"""Standalone op-by-op check against torch references (prints every error; exit 1 on failure).
+Run on the GPU box:  python tests/gpu_selfcheck.py"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gpinv_b200 import ops  # noqa: E402
+from oracle import gpinv_oracle as O  # noqa: E402
+
+dev = torch.device("cuda:0")
+FAIL = []
+
+
+def rel(a, b):
+    a = a.detach().cpu().double()
+    b = b.detach().cpu().double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-300))
+
+
+def report(name, err, tol):
+    ok = err <= tol and err == err
+    print("%-58s err=%.3e tol=%.1e %s" % (name, err, tol, "ok" if ok else "FAIL"), flush=True)
+    if not ok:
+        FAIL.append(name)
+
+
+def t(a):
+    return torch.as_tensor(a, dtype=torch.float64, device=dev)
+
+
+def check_gemm():
+    g = torch.Generator().manual_seed(0)
+    for (m, n, k) in [(8, 8, 4), (37, 53, 29), (128, 128, 16), (129, 257, 100), (300, 200, 1000), (1024, 512, 384)]:
+        for ta in (False, True):
+            for tb in (False, True):
+                A = torch.randn((k, m) if ta else (m, k), generator=g, dtype=torch.float64)
+                B = torch.randn((n, k) if tb else (k, n), generator=g, dtype=torch.float64)
+                ref = (A.T if ta else A) @ (B.T if tb else B)
+                out = ops.gemm(A.to(dev), B.to(dev), ta, tb, False)
+                report("gemm %dx%dx%d ta=%d tb=%d" % (m, n, k, ta, tb), rel(out, ref), 1e-13)
+    A = torch.randn(300, 77, generator=g, dtype=torch.float64)
+    out = ops.gemm(A.to(dev), A.to(dev), False, True, True)
+    report("gemm lower 300x300x77", rel(torch.tril(out), torch.tril(A @ A.T)), 1e-13)
+
+
+def check_kcore():
+    rng = np.random.RandomState(0)
+    for kind in ("rbf", "rbf_csym", "rbf_casym"):
+        for (n, n2, D, ard) in [(10, 11, 2, True), (33, 0, 1, False), (257, 130, 1, False), (100, 0, 3, True)]:
+            X = rng.randn(n, D)
+            X2 = rng.randn(n2, D) if n2 else None
+            ls = np.exp(0.3 * rng.randn(D)) if ard else np.array([0.7])
+            lst = torch.tensor(ls, requires_grad=True)
+            ref = O.kcore(kind, torch.tensor(X), None if X2 is None else torch.tensor(X2), lst)
+            if X2 is None:
+                ref = ref + 1e-6 * torch.eye(n, dtype=torch.float64)
+            W = torch.tensor(rng.randn(*ref.shape))
+            (gref,) = torch.autograd.grad((ref * W).sum(), lst)
+            lsd = t(ls).requires_grad_(True)
+            out = ops.kcore(t(X), None if X2 is None else t(X2), lsd, ops.MODE[kind], 1e-6 if X2 is None else 0.0)
+            (gout,) = torch.autograd.grad((out * W.to(dev)).sum(), lsd)
+            report("kcore %s n=%d n2=%d D=%d" % (kind, n, n2, D), rel(out, ref), 1e-14)
+            report("kcore_bwd %s n=%d n2=%d D=%d" % (kind, n, n2, D), rel(gout, gref), 1e-11)
+
+
+def spd(n, seed):
+    rng = np.random.RandomState(seed)
+    x = np.sort(rng.rand(n))[:, None] * 3.0
+    K = np.exp(-0.5 * (x - x.T) ** 2 / 0.5 ** 2) + 1e-4 * np.eye(n) + 0.05 * np.diag(rng.rand(n))
+    return K
+
+
+def check_potrf():
+    for n in (1, 5, 64, 65, 100, 256, 300, 515, 1024, 2048):
+        K = spd(n, n)
+        Kt = torch.tensor(K, requires_grad=True)
+        Lref = torch.linalg.cholesky(Kt)
+        Kjunk = K.copy()
+        Kd = t(Kjunk).requires_grad_(True)
+        L, info = ops.potrf(Kd)
+        report("potrf n=%d (info=%d)" % (n, int(info.item())), rel(L, Lref), 1e-12)
+        rng = np.random.RandomState(1)
+        Lbar = np.tril(rng.randn(n, n))
+        (gref,) = torch.autograd.grad((Lref * torch.tensor(Lbar)).sum(), Kt)
+        (gout,) = torch.autograd.grad((L * t(Lbar)).sum(), Kd)
+        report("potrf_bwd n=%d" % n, rel(gout, gref), 1e-9)
+    Kbad = spd(100, 3)
+    Kbad[70, 70] = -1.0
+    L, info = ops.potrf(t(Kbad))
+    report("potrf info on non-PD (info=%d)" % int(info.item()), 0.0 if int(info.item()) == 71 else 1.0, 0.5)
+
+
+def check_trsm():
+    for (m, n) in [(3, 5), (100, 64), (130, 200), (257, 515)]:
+        K = spd(n, 7)
+        L = np.linalg.cholesky(K)
+        B = np.random.RandomState(2).randn(m, n)
+        ref = torch.linalg.solve_triangular(torch.tensor(L), torch.tensor(B).T, upper=False).T
+        out = ops.trsm_rlt(t(L), t(B))
+        report("trsm_rlt m=%d n=%d" % (m, n), rel(out, ref), 1e-11)
+
+
+def check_sample():
+    rng = np.random.RandomState(3)
+    for (n, S, R, q_diag) in [(30, 10, 1, False), (150, 70, 2, False), (130, 33, 3, True), (300, 129, 1, False)]:
+        K = spd(n, 11)
+        Lc = np.linalg.cholesky(K)
+        sv = np.exp(0.2 * rng.randn(R))
+        q_mu = rng.randn(n, R)
+        mean = rng.randn(n, R)
+        E = rng.randn(R, S, n)
+        if q_diag:
+            q_sqrt = np.exp(0.3 * rng.randn(n, R))
+        else:
+            q_sqrt = 0.5 * np.eye(n)[:, :, None] + 0.1 * rng.randn(n, n, R)
+        # oracle
+        tl = [torch.tensor(a, requires_grad=True) for a in (Lc, sv, q_sqrt, q_mu, mean)]
+        Lc_t, sv_t, qs_t, qm_t, mn_t = tl
+        Lfull = torch.tril(Lc_t)[:, :, None] * sv_t[None, None, :]
+        f, KL = O.stvgp_sample(qm_t, qs_t, Lfull, mn_t, torch.tensor(E), q_diag)
+        Wf = torch.tensor(rng.randn(S, n, R))
+        obj = (f * Wf).sum() - 0.37 * KL
+        gref = torch.autograd.grad(obj, tl)
+        # device
+        dl = [t(a).requires_grad_(True) for a in (Lc, sv, q_sqrt, q_mu, mean)]
+        Lc_d, sv_d, qs_d, qm_d, mn_d = dl
+        Q = qs_d.T.contiguous() if q_diag else ops.tril_unpack(qs_d)
+        F, expF, kl, U = ops.stvgp_sample(Lc_d, sv_d, Q, qm_d.T.contiguous(), mn_d.T.contiguous(), t(E), q_diag, True)
+        fd = F.permute(1, 2, 0)
+        report("sample F n=%d S=%d R=%d diag=%d" % (n, S, R, q_diag), rel(fd, f), 1e-12)
+        report("sample expF", rel(expF, torch.exp(F)), 1e-14)
+        report("sample KL", rel(kl, KL.reshape(1)), 1e-12)
+        objd = (fd * Wf.to(dev)).sum() - 0.37 * kl.sum()
+        gout = torch.autograd.grad(objd, dl)
+        names = ["Lc", "sqrt_v", "q_sqrt", "q_mu", "mean"]
+        for nm, a, b in zip(names, gout, gref):
+            if nm == "Lc":
+                a, b = torch.tril(a), torch.tril(b)
+            report("sample_bwd d/d%s" % nm, rel(a, b), 1e-11)
+
+
+def check_liks():
+    rng = np.random.RandomState(4)
+    n, S, R = 70, 21, 2
+    F = rng.randn(R, S, n)
+    Y = rng.randn(n, R)
+    Ft = torch.tensor(F, requires_grad=True)
+    ref = ((Ft.permute(1, 2, 0) - torch.tensor(Y)[None]) ** 2).sum()
+    (gref,) = torch.autograd.grad(ref, Ft)
+    Fd = t(F).requires_grad_(True)
+    out = ops.gauss_sumsq(Fd, t(Y))
+    (gout,) = torch.autograd.grad(out.sum(), Fd)
+    report("gauss_sumsq", rel(out, ref.reshape(1)), 1e-13)
+    report("gauss_sumsq bwd", rel(gout, gref), 1e-13)
+    for (n, M, S) in [(30, 40, 10), (200, 333, 65)]:
+        r = np.linspace(0, 1, n)
+        z = np.linspace(-0.9, 0.9, M)
+        A = O.make_los_matrix(r, z)
+        F = 0.3 * rng.randn(S, n)
+        Y = rng.randn(M)
+        Ft = torch.tensor(F, requires_grad=True)
+        P = torch.exp(Ft) @ torch.tensor(A).T
+        ref = ((torch.tensor(Y)[None] - P) ** 2).sum()
+        (gref,) = torch.autograd.grad(ref, Ft)
+        Fd = t(F).requires_grad_(True)
+        ss, Rs = ops.abel_resid(Fd, torch.exp(Fd).detach(), t(A), t(Y))
+        (gout,) = torch.autograd.grad(ss.sum(), Fd)
+        report("abel_resid n=%d M=%d S=%d" % (n, M, S), rel(ss, ref.reshape(1)), 1e-13)
+        report("abel_resid bwd", rel(gout, gref), 1e-12)
+    x = rng.randn(100001)
+    report("sumsq", rel(ops.sumsq(t(x)), torch.tensor([np.sum(x * x)])), 1e-13)
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    for fn in (check_gemm, check_kcore, check_potrf, check_trsm, check_sample, check_liks):
+        try:
+            fn()
+            torch.cuda.synchronize()
+        except Exception as e:  # keep going so one broken op does not hide the others
+            import traceback
+            traceback.print_exc()
+            FAIL.append(fn.__name__ + ": " + repr(e)[:200])
+    print("elapsed %.1fs; %d failures" % (time.time() - t0, len(FAIL)))
+    for f in FAIL:
+        print("FAILED:", f)
+    sys.exit(1 if FAIL else 0)
