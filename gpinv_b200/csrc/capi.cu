@@ -1,4 +1,5 @@
 // extern "C" surface of libgpinv_sm100.so (declared in include/gpinv_b200.h).
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -19,6 +20,8 @@ int potrf_f64(double*, int, int, int*, cudaStream_t);
 size_t potrf_bwd_ws_bytes(int);
 int potrf_bwd_f64(const double*, int, double*, int, int, double*, cudaStream_t);
 int trsm_rlt_f64(const double*, int, double*, int, int, int, cudaStream_t);
+size_t potrf_bwd_inv_ws_bytes(int);
+int potrf_bwd_inv_f64(const double*, int, double*, int, int, double*, cudaStream_t);
 int tril_unpack_f64(const double*, double*, int, int, cudaStream_t);
 int tril_pack_f64(const double*, double*, int, int, cudaStream_t);
 int sumsq_f64(const double*, size_t, double*, cudaStream_t);
@@ -66,12 +69,25 @@ int gpinv_potrf_f64(double* A, int n, int lda, int* info, void* stream) {
   return potrf_f64(A, n, lda, info, ST(stream));
 }
 
-size_t gpinv_potrf_bwd_ws_bytes(int n) { return potrf_bwd_ws_bytes(n); }
+static bool use_murray() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GPINV_POTRF_BWD");
+    v = (e && strcmp(e, "murray") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+size_t gpinv_potrf_bwd_ws_bytes(int n) {
+  const size_t a = potrf_bwd_ws_bytes(n), b = potrf_bwd_inv_ws_bytes(n);
+  return a > b ? a : b;
+}
 
 int gpinv_potrf_bwd_f64(const double* L, int ldl, double* Abar, int ldab, int n, void* ws,
                         void* stream) {
   if (n <= 0 || ldl < n || ldab < n) return GPINV_ERR_ARG;
-  return potrf_bwd_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
+  if (use_murray()) return potrf_bwd_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
+  return potrf_bwd_inv_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
 }
 
 int gpinv_trsm_rlt_f64(const double* L, int ldl, double* X, int ldx, int m, int n, void* stream) {

@@ -98,4 +98,20 @@ int gemm_simple(int la, int lb, int M, int N, int K, double alpha, const double*
   return gemm_launch(la, lb, ef, p, stream);
 }
 
+int gemm_batched(int la, int lb, int M, int N, int K, double alpha, const double* A, int lda,
+                 long long strideA, const double* B, int ldb, long long strideB, double beta,
+                 double* C, int ldc, long long strideC, int batch, bool lower, int kmode,
+                 cudaStream_t stream) {
+  if (batch <= 0) return GPINV_OK;
+  GemmParams p = {};
+  p.A = A; p.B = B; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb;
+  p.alpha = alpha; p.beta = beta; p.Cin = C; p.ldcin = ldc; p.out = C; p.ldo = ldc;
+  p.kmode = kmode; p.splitk = 1;
+  p.batch = batch; p.strideA = strideA; p.strideB = strideB; p.strideO = strideC;
+  p.strideCin = strideC;
+  unsigned ef = EF_BETA;
+  if (lower) ef |= EF_LOWER;
+  return gemm_launch(la, lb, ef, p, stream);
+}
+
 }  // namespace gpinv

@@ -53,7 +53,7 @@ struct GemmParams {
   double* sumsq;
   double* colsum;
   double* dot;
-  int kmode;   // 0 full | 1: k < n0+BN | 2: k >= n0 | 3: k < m0+BM | 4: k >= m0
+  int kmode;   // 0 full | 1: k < n0+BN | 2: k >= n0 | 3: k < m0+BM | 4: k >= m0 | 5: n0 <= k < m0+BM
   int splitk;  // >= 1
   int tiles_m, tiles_n;
   int vecA, vecB, vecO;  // 16-byte alignment of operands / output rows
@@ -147,7 +147,13 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
   int tm, tn;
   {
     const int idx = blockIdx.x;
-    if (EF & EF_LOWER) {
+    if ((EF & EF_LOWER) && p.kmode == 5) {
+      // work grows with the distance from the diagonal: enumerate far diagonals first
+      int d = p.tiles_m - 1, rem = idx;
+      while (rem >= p.tiles_m - d) { rem -= p.tiles_m - d; --d; }
+      tn = rem;
+      tm = rem + d;
+    } else if (EF & EF_LOWER) {
       int r = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
       while ((r + 1) * (r + 2) / 2 <= idx) ++r;
       while (r * (r + 1) / 2 > idx) --r;
@@ -175,6 +181,7 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
   else if (p.kmode == 2) kb = (n0 / BK) * BK;
   else if (p.kmode == 3) ke = min(p.K, m0 + BM);
   else if (p.kmode == 4) kb = (m0 / BK) * BK;
+  else if (p.kmode == 5) { kb = (n0 / BK) * BK; ke = min(p.K, m0 + BM); }
   int ktiles = (ke > kb) ? (ke - kb + BK - 1) / BK : 0;
   if (p.splitk > 1) {
     const int per = (ktiles + p.splitk - 1) / p.splitk;
@@ -266,7 +273,11 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
       for (int e = 0; e < 2; ++e) {
         const int c = col + e;
         ok[e] = (row < p.M) && (c < p.N);
-        if (EF & EF_LOWER) ok[e] = ok[e] && (c <= row);
+        bool upper = false;
+        if (EF & EF_LOWER) {
+          upper = ok[e] && (c > row);
+          ok[e] = ok[e] && (c <= row);
+        }
         double x = alpha * acc[i][j][e];
         if (ok[e]) {
           if (EF & EF_DOT) r_dot += x * __ldg(p.W + (size_t)row * p.ldw + c);
@@ -277,6 +288,11 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
           if (EF & EF_COLSUM) r_col[j][e] += x;
         }
         v[e] = x;
+        // strict upper part of a diagonal tile: store exact zeros so the result is a clean tril()
+        if ((EF & EF_LOWER) && !(EF & EF_ATOMIC) && upper && p.out) {
+          v[e] = 0.0;
+          p.out[(size_t)row * p.ldo + c] = 0.0;
+        }
       }
       if (EF & EF_ATOMIC) {
         if (ok[0]) atomicAdd(p.out + (size_t)row * p.ldo + col, v[0]);
@@ -329,5 +345,11 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream);
 int gemm_simple(int la, int lb, int M, int N, int K, double alpha, const double* A, int lda,
                 const double* B, int ldb, double beta, double* C, int ldc, bool lower, int kmode,
                 int splitk, cudaStream_t stream);
+
+// Batched variant (blockIdx.z) with element strides between consecutive problems.
+int gemm_batched(int la, int lb, int M, int N, int K, double alpha, const double* A, int lda,
+                 long long strideA, const double* B, int ldb, long long strideB, double beta,
+                 double* C, int ldc, long long strideC, int batch, bool lower, int kmode,
+                 cudaStream_t stream);
 
 }  // namespace gpinv

@@ -1,0 +1,231 @@
+"""Model base: the upward interface that optimisers and samplers call.
+
+In the reference this layer is GPflow's ``Model`` (``_compile`` / ``_objective`` / ``optimize``
+/ ``sample``; GPinv's own clone of the pattern is GPinv/model.py:23-91,148-240).  Here
+``_objective(x)`` evaluates ``build_likelihood() + build_prior()`` with the sm_100a ops and
+their hand-written backward passes and returns ``(-f, -df/dx)`` exactly like GPflow's
+closure (usage: notebooks/Abel_inversion.ipynb:416-418).
+
+``x`` may be a numpy vector (reference behaviour: host in, host out — one H2D copy of ``x`` and
+one D2H copy of the gradient) or a CUDA tensor (device-resident: nothing leaves HBM and
+nothing synchronises).
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+import torch
+
+from . import hmc
+from .param import Parameterized, default_device
+
+
+class OptimizeResult(dict):
+    __getattr__ = dict.__getitem__
+
+
+class Model(Parameterized):
+    def __init__(self, name="model"):
+        Parameterized.__init__(self)
+        self._name = name
+        self._pending_infos = []
+        self.dist = None            # set by gpinv_b200.dist.attach()
+        self._pinned = {}
+
+    # ---- to be provided by subclasses ----------------------------------------------
+    def build_likelihood(self, **kw):
+        raise NotImplementedError
+
+    def _prepare(self):
+        """Hook called before every evaluation (StVGP re-creates q_mu/q_sqrt when X changed)."""
+
+    # ---- objective -------------------------------------------------------------------
+    def _objective_device(self, x: torch.Tensor, **kw):
+        """(-f, -df/dx) as CUDA tensors ([1] and [|x|]); no host synchronisation."""
+        self._prepare()
+        leaves = self.make_tensors(x)
+        self._pending_infos = []
+        try:
+            with self.tensor_mode():
+                f = self.build_likelihood(**kw)
+                prior = self.build_prior()
+                if prior is not None:
+                    f = f + (prior if self.dist is None else prior / self.dist.world_size)
+            nf = -f.reshape(())          # differentiate -f: the gradients come out already negated
+            grads = torch.autograd.grad(nf, leaves, allow_unused=True)
+        finally:
+            self.clear_tensors()
+        parts = []
+        for g, leaf in zip(grads, leaves):
+            parts.append(torch.zeros(leaf.numel(), dtype=torch.float64, device=x.device) if g is None
+                         else g.reshape(-1))
+        buf = torch.cat([nf.detach().reshape(1)] + parts)
+        if self.dist is not None:
+            self.dist.all_reduce(buf)
+        return buf[:1], buf[1:]
+
+    def _check_infos(self):
+        infos, self._pending_infos = self._pending_infos, []
+        for info in infos:
+            i = int(info.item())
+            if i != 0:
+                raise RuntimeError("Cholesky decomposition was not successful: the matrix is not "
+                                   "positive definite at pivot %d" % i)
+
+    def _objective(self, x, **kw):
+        """numpy in -> (float, numpy) out; CUDA tensor in -> (tensor[1], tensor) out."""
+        if isinstance(x, torch.Tensor):
+            return self._objective_device(x, **kw)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        dev = default_device()
+        n = x.size
+        pin = self._pinned.get(n)
+        if pin is None:
+            pin = (torch.empty(n, dtype=torch.float64).pin_memory(),
+                   torch.empty(n + 1, dtype=torch.float64).pin_memory())
+            self._pinned = {n: pin}
+        hin, hout = pin
+        hin.numpy()[...] = x
+        xd = hin.to(dev, non_blocking=True)
+        f, g = self._objective_device(xd, **kw)
+        hout[:1].copy_(f, non_blocking=True)
+        hout[1:].copy_(g, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self._check_infos()
+        out = hout.numpy()
+        return float(out[0]), out[1:].copy()
+
+    def compute_log_likelihood(self, **kw):
+        x = torch.as_tensor(self.get_free_state()).to(default_device())
+        self._prepare()
+        self.make_tensors(x)
+        try:
+            with self.tensor_mode(), torch.no_grad():
+                f = self.build_likelihood(**kw)
+        finally:
+            self.clear_tensors()
+        return float(f.reshape(-1)[0].item())
+
+    def compute_log_prior(self):
+        x = torch.as_tensor(self.get_free_state()).to(default_device())
+        self.make_tensors(x)
+        try:
+            with self.tensor_mode(), torch.no_grad():
+                p = self.build_prior()
+        finally:
+            self.clear_tensors()
+        return 0.0 if p is None else float(p.item())
+
+    # ---- evaluate a method in tensor mode at the current state (GPflow AutoFlow) ---------
+    def _run(self, fn, *args, **kw):
+        self._prepare()
+        x = torch.as_tensor(self.get_free_state()).to(default_device())
+        self.make_tensors(x)
+        try:
+            with self.tensor_mode(), torch.no_grad():
+                out = fn(*args, **kw)
+        finally:
+            self.clear_tensors()
+        self._check_infos()
+        if isinstance(out, tuple):
+            return tuple(o.detach().cpu().numpy() for o in out)
+        return out.detach().cpu().numpy()
+
+    # ---- optimisation ------------------------------------------------------------------
+    def optimize(self, method="L-BFGS-B", tol=None, callback=None, maxiter=1000, **kw):
+        """``method`` is a scipy method name or an optimizer descriptor from ``gpinv_b200.train``
+        (the reference takes a ``tf.train`` optimizer there).  Signature mirrored from
+        GPinv/model.py:94-95."""
+        self._prepare()
+        if isinstance(method, str):
+            return self._optimize_np(method, tol, callback, maxiter, **kw)
+        return self._optimize_torch(method, callback, maxiter, **kw)
+
+    def _optimize_np(self, method, tol, callback, maxiter, **kw):
+        from scipy.optimize import minimize
+        options = dict(disp=False, maxiter=maxiter)
+        if "max_iters" in kw:
+            options["maxiter"] = kw.pop("max_iters")
+        options.update(kw)
+        state = {"x": self.get_free_state()}
+
+        def obj(x):
+            f, g = self._objective(x)
+            if np.isfinite(f) and np.all(np.isfinite(g)):
+                state["x"] = x.copy()
+            else:  # GPflow's ObjectiveWrapper: keep the optimiser alive on a failed evaluation
+                return 1e100 if not np.isfinite(f) else f, np.where(np.isfinite(g), g, 0.0)
+            return f, g
+
+        try:
+            result = minimize(fun=obj, x0=self.get_free_state(), method=method, jac=True, tol=tol,
+                              callback=callback, options=options)
+            self.set_state(result.x)
+        except KeyboardInterrupt:
+            print("Caught KeyboardInterrupt, setting model with most recent state.")
+            self.set_state(state["x"])
+            return None
+        return result
+
+    def _optimize_torch(self, method, callback, maxiter, **kw):
+        dev = default_device()
+        x = torch.as_tensor(self.get_free_state()).to(dev)
+        x.requires_grad_(False)
+        param = torch.nn.Parameter(x, requires_grad=True)
+        if hasattr(method, "make"):
+            opt = method.make([param])
+        elif isinstance(method, type) and issubclass(method, torch.optim.Optimizer):
+            opt = method([param], **kw)
+        elif callable(method):
+            opt = method([param])
+        else:
+            raise ValueError("unsupported optimizer %r" % (method,))
+        f = None
+        it = 0
+        try:
+            while it < maxiter:
+                f, g = self._objective_device(param.data)
+                param.grad = g
+                opt.step()
+                if callback is not None:
+                    callback(param.data.detach().cpu().numpy())
+                it += 1
+        except KeyboardInterrupt:
+            print("Caught KeyboardInterrupt, setting model with most recent state.")
+        xf = param.data.detach().cpu().numpy()
+        self._check_infos()
+        self.set_state(xf)
+        fun, jac = self._objective(xf)
+        return OptimizeResult(fun=fun, jac=jac, x=xf, nit=it, success=True, status="Finished iterations.")
+
+    # ---- HMC (GPflow Model.sample -> hmc.sample_HMC) -----------------------------------------
+    def sample(self, num_samples, Lmax=20, epsilon=0.01, thin=1, burn=0, verbose=False,
+               return_logprobs=False, RNG=None):
+        self._prepare()
+        if RNG is None:
+            RNG = np.random.RandomState(0)
+        return hmc.sample_HMC(self._objective, num_samples, Lmax=Lmax, epsilon=epsilon, thin=thin,
+                              burn=burn, x0=self.get_free_state(), verbose=verbose,
+                              return_logprobs=return_logprobs, RNG=RNG)
+
+
+class GPModel(Model):
+    """GPflow ``GPModel``: holds X, Y, kern, likelihood, mean_function; ``predict_f``."""
+
+    def __init__(self, X, Y, kern, likelihood, mean_function, name="model"):
+        Model.__init__(self, name)
+        self.kern, self.likelihood, self.mean_function = kern, likelihood, mean_function
+        self.X, self.Y = X, Y
+
+    def build_predict(self, Xnew, full_cov=False):
+        raise NotImplementedError
+
+    def predict_f(self, Xnew):
+        """(mean [n2,R], var [n2,R]) at the current state (GPflow AutoFlow'd predict_f)."""
+        Xn = torch.as_tensor(np.ascontiguousarray(Xnew, dtype=np.float64)).to(default_device())
+        return self._run(self.build_predict, Xn)
+
+    def predict_f_full_cov(self, Xnew):
+        Xn = torch.as_tensor(np.ascontiguousarray(Xnew, dtype=np.float64)).to(default_device())
+        return self._run(self.build_predict, Xn, full_cov=True)

@@ -1,0 +1,154 @@
+"""StVGP: stochastic approximation of the variational Gaussian process (mirror of
+GPinv/stvgp.py).  ``build_likelihood`` / ``_sample`` read like the reference's graph code; the
+arithmetic runs in the sm_100a ops of ``gpinv_b200.ops``.
+
+One deliberate extension of the reference interface: ``_objective(x, eps=...)`` accepts the
+standard-normal draws ``eps`` [R,S,n] (the reference draws them inside the TF graph,
+GPinv/stvgp.py:164, which makes its ELBO irreproducible across calls); ``seed=`` fixes the
+device Philox stream instead.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import conditionals, ops, transforms
+from .mean_functions import Zero
+from .model import GPModel
+from .param import DataHolder, Param, default_device
+
+
+class StVGP(GPModel):
+    def __init__(self, X, Y, kern, likelihood, mean_function=None, num_latent=None,
+                 q_diag=False, KL_analytic=False, num_samples=20, seed=None):
+        """Arguments as GPinv/stvgp.py:38-50.  X [n,D]; Y any shape the likelihood accepts
+        (``num_latent`` must be given when Y is not [n,R])."""
+        self.num_data = X.shape[0]
+        self.num_latent = num_latent or Y.shape[1]
+        self.num_samples = num_samples
+        if mean_function is None:
+            mean_function = Zero(self.num_latent)
+        Y = DataHolder(Y, on_shape_change="recompile")
+        X = DataHolder(X, on_shape_change="recompile")
+        GPModel.__init__(self, X, Y, kern, likelihood, mean_function)
+        self.q_diag = q_diag
+        self.KL_analytic = KL_analytic
+        self._init_variational()
+        self._generator = None
+        self._seed = seed
+        self._KL = None
+
+    def _init_variational(self):
+        """GPinv/stvgp.py:62-74: q_mu = 0; q_sqrt = I per latent (no transform) or ones (positive)."""
+        self.q_mu = Param(np.zeros((self.num_data, self.num_latent)))
+        if self.q_diag:
+            self.q_sqrt = Param(np.ones((self.num_data, self.num_latent)), transforms.positive)
+        else:
+            q_sqrt = np.array([np.eye(self.num_data) for _ in range(self.num_latent)]).swapaxes(0, 2)
+            self.q_sqrt = Param(q_sqrt)
+
+    def _prepare(self):
+        """GPinv/stvgp.py:76-94: re-create the variational parameters when X changed size."""
+        n = object.__getattribute__(self, "X").shape[0]
+        if self.num_data != n:
+            self.num_data = n
+            self._init_variational()
+
+    def _draw_eps(self, S):
+        dev = default_device()
+        if self._generator is None:
+            self._generator = torch.Generator(device=dev)
+            if self._seed is not None:
+                self._generator.manual_seed(int(self._seed))
+            else:
+                self._generator.seed()
+        return torch.randn((self.num_latent, S, self.num_data), dtype=torch.float64, device=dev,
+                           generator=self._generator)
+
+    def _eps_tensor(self, eps, S):
+        if eps is None:
+            eps = self._draw_eps(S)
+        elif not isinstance(eps, torch.Tensor):
+            eps = torch.as_tensor(np.ascontiguousarray(eps, dtype=np.float64)).to(default_device())
+        if self.dist is not None:
+            eps = self.dist.shard_samples(eps)
+        return eps.contiguous()
+
+    def build_likelihood(self, eps=None):
+        """Variational lower bound with stochastic approximation (GPinv/stvgp.py:96-107)."""
+        S_global = self.num_samples if eps is None else eps.shape[1]
+        eps = self._eps_tensor(eps, S_global)
+        f_samples, expF = self._sample(eps)
+        lik = self.likelihood.logp_sum(f_samples, self.Y, expF=expF)
+        share = 1.0 if self.dist is None else 1.0 / self.dist.world_size
+        if not self.KL_analytic:
+            return (lik - self._KL) / S_global
+        return lik / S_global - share * self._analytical_KL()
+
+    def build_predict(self, Xnew, full_cov=False):
+        """GPinv/stvgp.py:109-122."""
+        mu, var = conditionals.conditional(Xnew, self.X, self.kern, self.q_mu,
+                                           q_sqrt=self.q_sqrt, full_cov=full_cov, whiten=True)
+        return mu + self.mean_function(Xnew), var
+
+    def sample_F(self, n_sample):
+        """Samples of the transformed latent function, [n_sample, ...] (GPinv/stvgp.py:124-132)."""
+        def fn():
+            f, _ = self._sample(self._eps_tensor(None, int(n_sample)))
+            return self.likelihood.sample_F(f)
+        return self._run(fn)
+
+    def sample_Y(self, n_sample):
+        """GPinv/stvgp.py:134-142."""
+        def fn():
+            f, _ = self._sample(self._eps_tensor(None, int(n_sample)))
+            return self.likelihood.sample_Y(f)
+        return self._run(fn)
+
+    def _sample(self, eps):
+        """f = mean + L (q_mu + tril(q_sqrt) eps) for every draw; stores the stochastic KL in
+        ``self._KL`` (GPinv/stvgp.py:144-185).  Returns ([S,n,R] views of) F and exp(F)."""
+        R = self.num_latent
+        chol = self.kern.Cholesky_factor(self.X)
+        self._pending_infos += chol.infos
+        mean = self.mean_function(self.X).T.contiguous()          # [R,n]
+        q_mu = self.q_mu.T.contiguous()                            # [R,n]
+        if self.q_diag:
+            Q = self.q_sqrt.T.contiguous()                         # [R,n]
+        else:
+            Q = ops.tril_unpack(self.q_sqrt)                       # [R,n,n], zeros above diag
+        want_exp = bool(getattr(self.likelihood, "wants_expF", False))
+        Fs, Es, KLs = [], [], []
+        for core, r0, r1 in chol.groups():
+            if chol.kron:
+                from . import kronecker
+                F, expF, KL = kronecker.kron_sample(core, chol.sqrt_var[r0:r1], Q[r0:r1], q_mu[r0:r1],
+                                                    mean[r0:r1], eps[r0:r1], self.q_diag, want_exp)
+            else:
+                F, expF, KL, _ = ops.stvgp_sample(core, chol.sqrt_var[r0:r1].contiguous(), Q[r0:r1],
+                                                  q_mu[r0:r1], mean[r0:r1], eps[r0:r1],
+                                                  self.q_diag, want_exp)
+            Fs.append(F)
+            Es.append(expF)
+            KLs.append(KL)
+        F = Fs[0] if len(Fs) == 1 else torch.cat(Fs, 0)
+        expF = None
+        if want_exp:
+            expF = (Es[0] if len(Es) == 1 else torch.cat(Es, 0)).permute(1, 2, 0)
+        KL = KLs[0]
+        for k in KLs[1:]:
+            KL = KL + k
+        self._KL = KL
+        return F.permute(1, 2, 0), expF
+
+    def _analytical_KL(self):
+        """GPinv/stvgp.py:187-195 -> GPflow gauss_kl_white[_diag]."""
+        q_mu, q_sqrt = self.q_mu, self.q_sqrt
+        KL = 0.5 * torch.sum(torch.square(q_mu)) - 0.5 * float(q_mu.numel())
+        if self.q_diag:
+            KL = KL - 0.5 * torch.sum(torch.log(torch.square(q_sqrt))) + 0.5 * torch.sum(torch.square(q_sqrt))
+        else:
+            Q = ops.tril_unpack(q_sqrt)
+            diag = torch.diagonal(Q, dim1=1, dim2=2)
+            KL = KL - 0.5 * torch.sum(torch.log(torch.square(diag))) + 0.5 * torch.sum(torch.square(Q))
+        return KL

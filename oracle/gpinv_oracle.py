@@ -558,7 +558,7 @@ def objective(spec, x, eps=None) -> Tuple[float, np.ndarray]:
     xt = _t(x).clone().requires_grad_(True)
     f = objective_value(spec, xt, eps)
     (g,) = torch.autograd.grad(f, xt)
-    return -float(f), -g.numpy()
+    return -float(f.detach()), -g.numpy()
 
 
 def predict_f(spec, x, Xnew, full_cov=False):

@@ -1,0 +1,73 @@
+"""Generates the golden fixtures tests/golden/*.npz with the CPU oracle.
+
+The reference itself cannot run here (TF<=0.11 / GPflow 0.3 are not installable),
+so these vectors are outputs of the oracle restatement, which is pinned separately by the
+published golden value and identities in tests/test_oracle.py.  Re-run:
+    python -m tests.golden.make_golden
+Each file: x (free state), eps [R,S,n] (absent for GPMC), f = -objective, g = -gradient."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import gpinv_oracle as O  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = ["abel_stvgp_n30", "gauss_stvgp_n40", "gauss_stvgp_qdiag_klanalytic", "abel_gpmc_n30", "spec_stack_n12"]
+
+
+def _abel(n, M):
+    from tests.helpers import abel_data
+    return abel_data(n, M)
+
+
+def build_spec(name):
+    if name == "abel_stvgp_n30" or name == "abel_gpmc_n30":
+        r, z, A, y = _abel(30, 40)
+        return dict(model="stvgp" if "stvgp" in name else "gpmc", X=r[:, None], Y=y[:, None],
+                    kern=dict(type="rbf_csym", input_dim=1, output_dim=1, ARD=False),
+                    mean=dict(type="constant", output_dim=1), lik=dict(type="abel", A=A), num_latent=1)
+    if name.startswith("gauss_stvgp"):
+        X = np.linspace(0, 6, 40)[:, None]
+        Y = np.sin(X) + 0.3 * np.random.RandomState(0).randn(40, 1)
+        extra = dict(q_diag=True, KL_analytic=True) if "qdiag" in name else {}
+        return dict(model="stvgp", X=X, Y=Y, kern=dict(type="rbf", input_dim=1, output_dim=1, ARD=False),
+                    mean=dict(type="zero", output_dim=1), lik=dict(type="gaussian"), num_latent=1, **extra)
+    if name == "spec_stack_n12":
+        from tests.helpers import spec_data
+        r, A, cosT, lam, y = spec_data(12, 9, 7)
+        return dict(model="stvgp", X=r[:, None], Y=y,
+                    kern=dict(type="stack", kern_list=[
+                        dict(type="rbf_csym", input_dim=1, output_dim=2, ARD=False),
+                        dict(type="rbf_casym", input_dim=1, output_dim=1, ARD=False)]),
+                    mean=dict(type="stack", mean_list=[dict(type="constant", output_dim=2),
+                                                       dict(type="zero", output_dim=1)]),
+                    lik=dict(type="spec_abel", A=A, cosT=cosT, lam=lam), num_latent=3)
+    raise KeyError(name)
+
+
+def main():
+    for i, name in enumerate(CASES):
+        spec = build_spec(name)
+        rng = np.random.RandomState(10 + i)
+        n, R = spec["X"].shape[0], spec["num_latent"]
+        size = O.state_size(spec)
+        x = 0.2 * rng.randn(size)
+        if spec["model"] == "stvgp" and not spec.get("q_diag", False):
+            x[size - n * n * R:] += np.stack([np.eye(n)] * R, -1).ravel()
+        out = dict(x=x)
+        eps = None
+        if spec["model"] == "stvgp":
+            eps = rng.randn(R, 6, n)
+            out["eps"] = eps
+        f, g = O.objective(spec, x, eps)
+        out.update(f=np.float64(f), g=g)
+        np.savez(os.path.join(HERE, name + ".npz"), **out)
+        print(name, size, f, np.linalg.norm(g))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,85 @@
+"""Test helpers: build the oracle's plain-dict description of a gpinv_b200 model, and the
+synthetic configurations of SURVEY.md 8(d)."""
+import numpy as np
+
+from gpinv_b200 import kernels, kronecker, likelihoods, mean_functions
+from oracle import gpinv_oracle as O
+
+
+def _kern_spec(k):
+    if isinstance(k, kernels.Stack):
+        return {"type": "stack", "kern_list": [_kern_spec(s) for s in k.kern_list._list]}
+    base = {"input_dim": k.input_dim, "output_dim": k.output_dim, "ARD": k.ARD,
+            "active_dims": None if isinstance(k.active_dims, slice) else list(k.active_dims)}
+    if isinstance(k, kronecker.RBF2D):
+        base.update(type="rbf2d", dim1=k.dim1.value, dim2=k.dim2.value)
+    elif isinstance(k, kernels.RBF_csym):
+        base["type"] = "rbf_csym"
+    elif isinstance(k, kernels.RBF_casym):
+        base["type"] = "rbf_casym"
+    else:
+        base["type"] = "rbf"
+    return base
+
+
+def _mean_spec(m):
+    if isinstance(m, mean_functions.Stack):
+        return {"type": "stack", "mean_list": [_mean_spec(s) for s in m.mean_list._list]}
+    if isinstance(m, mean_functions.Constant):
+        return {"type": "constant", "output_dim": m.output_dim}
+    return {"type": "zero", "output_dim": m.output_dim}
+
+
+def _lik_spec(l):
+    if isinstance(l, likelihoods.AbelLikelihood):
+        return {"type": "abel", "A": l.Amat.value}
+    if isinstance(l, likelihoods.SpecAbelLikelihood):
+        return {"type": "spec_abel", "A": l.Amat.value, "cosT": l.cosT.value, "lam": l.lam.value}
+    return {"type": "gaussian"}
+
+
+def spec_from_model(m):
+    is_st = hasattr(m, "q_mu")
+    return {
+        "model": "stvgp" if is_st else "gpmc",
+        "X": m.X.value, "Y": m.Y.value,
+        "kern": _kern_spec(m.kern), "mean": _mean_spec(m.mean_function), "lik": _lik_spec(m.likelihood),
+        "num_latent": m.num_latent,
+        "q_diag": getattr(m, "q_diag", False), "KL_analytic": getattr(m, "KL_analytic", False),
+    }
+
+
+def abel_data(n, M, seed=0):
+    """SURVEY.md 8(d) cfg1/cfg5 generator (notebooks/Abel_inversion.ipynb:115-120,183-185)."""
+    r = np.linspace(0, 1., n)
+    z = np.linspace(-0.9, 0.9, M)
+    A = O.make_los_matrix(r, z)
+    g = np.exp(-(r - 0.3) ** 2 / 0.1) + np.exp(-(r + 0.3) ** 2 / 0.1)
+    y = A @ g + 0.1 * np.random.RandomState(seed).randn(M)
+    return r, z, A, y
+
+
+def spec_data(n, M, nlam, seed=0):
+    """Spectroscopic notebook generator (Spectroscopic_Abel_inversion.ipynb:112-119,224-243)."""
+    r = np.linspace(0, 1., n)
+    a = np.exp(-(r - 0.3) ** 2 / 0.1) + np.exp(-(r + 0.3) ** 2 / 0.1)
+    v = 3. * np.exp(-(r - 0.6) ** 2 / 0.05) * (r - 0.6)
+    sigma = 1. * np.exp(-r * r / 0.3) + 0.2
+    z = np.linspace(-0.9, 0.9, M)
+    A = O.make_los_matrix(r, z)
+    cosT = O.make_cos_theta(r, z)
+    lam = np.linspace(-3, 3, nlam)
+    f = a[None, None, :] / (np.sqrt(2 * np.pi) * sigma[None, None, :]) * np.exp(
+        -0.5 * ((lam[:, None, None] - v[None, None, :] * cosT[None]) / sigma[None, None, :]) ** 2)
+    y = np.sum(A[None] * f, 2) + 0.02 * np.random.RandomState(seed).randn(nlam, M)
+    return r, A, cosT, lam, y
+
+
+def perturbed_state(m, scale=0.1, seed=1):
+    x0 = m.get_free_state()
+    return x0 + scale * np.random.RandomState(seed).randn(x0.size)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))

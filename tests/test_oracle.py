@@ -1,0 +1,155 @@
+"""CPU tests that pin the oracle (oracle/gpinv_oracle.py) before it is trusted as the checker:
+G1 published golden value, G2 zero-variance identity, G4 explicit-loop kernels, G5 MC
+consistency, geometry and layout checks."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gpinv_oracle as O
+
+
+def test_G1_published_golden_value():
+    # notebooks/Stochastic_approximation_demo.ipynb:142-150
+    X = np.linspace(0, 6, 40)[:, None]
+    Y = np.sin(X) + 0.3 * np.random.RandomState(0).randn(40, 1)
+    f = O.gpr_nlml([1.36444855, -0.21198308, -2.20949039], X, Y)
+    assert abs(f - 19.49947035345194) / 19.49947035345194 < 1e-9   # x is printed to 8 digits
+
+
+def test_G1_transform_offset_matters():
+    X = np.linspace(0, 6, 40)[:, None]
+    Y = np.sin(X) + 0.3 * np.random.RandomState(0).randn(40, 1)
+    x = np.array([1.36444855, -0.21198308, -2.20949039])
+    # a different parameter order is off by far more than the golden tolerance
+    assert abs(O.gpr_nlml(x[[1, 0, 2]], X, Y) - 19.49947035345194) > 1.0
+
+
+def _exact_posterior(X, Y, ls, v, s2):
+    n = X.shape[0]
+    core = O.kcore("rbf", O._t(X), None, O._t([ls])) + O.JITTER * torch.eye(n, dtype=O.DT)
+    L = torch.linalg.cholesky(core) * np.sqrt(v)
+    Sinv = torch.eye(n, dtype=O.DT) + L.T @ L / s2
+    Sst = torch.linalg.inv(Sinv)
+    m = Sst @ L.T @ torch.tensor(Y) / s2
+    q_sqrt = torch.linalg.cholesky(Sst)
+    K = L @ L.T + s2 * torch.eye(n, dtype=O.DT)
+    Lk = torch.linalg.cholesky(K)
+    a = torch.linalg.solve_triangular(Lk, torch.tensor(Y), upper=False)
+    logml = float(-0.5 * torch.sum(a * a) - torch.sum(torch.log(torch.diagonal(Lk))) - 0.5 * n * O.LOG2PI)
+    return m.numpy(), q_sqrt.numpy(), logml
+
+
+@pytest.mark.parametrize("S", [1, 3, 10])
+def test_G2_zero_variance_identity(S):
+    rng = np.random.RandomState(0)
+    X = np.linspace(0., 1., 20)[:, None]
+    Y = (np.sin(3. * X[:, 0]) + rng.randn(20) * 0.1)[:, None]
+    ls, v, s2 = 0.55, 0.9, 0.007
+    m, q_sqrt, logml = _exact_posterior(X, Y, ls, v, s2)
+    spec = dict(model="stvgp", X=X, Y=Y, kern=dict(type="rbf", input_dim=1, output_dim=1, ARD=False),
+                mean=dict(type="zero", output_dim=1), lik=dict(type="gaussian"), num_latent=1)
+    x = O.pack_constrained(spec, {"kern.lengthscales": [ls], "kern.variance": [v],
+                                  "likelihood.variance": [s2], "q_mu": m, "q_sqrt": q_sqrt[:, :, None]})
+    eps = np.random.RandomState(100 + S).randn(1, S, 20)
+    f, _ = O.objective(spec, x, eps)
+    assert abs(-f - logml) < 1e-9 * abs(logml)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "rbf_csym", "rbf_casym"])
+def test_G4_kernels_against_explicit_loops(kind):
+    # fixture of testing/test_kernels.py:82-95
+    rng = np.random.RandomState(0)
+    var = np.exp(rng.randn(3))
+    X, X2 = rng.randn(10, 2), rng.randn(11, 2)
+    ls = np.array([0.7, 1.3])
+    for a, b in ((X, None), (X, X2)):
+        got = O.kern_K(kind, torch.tensor(a), None if b is None else torch.tensor(b),
+                       O._t(ls), O._t(var)).numpy()
+        ref = O.loop_core(kind, a, b, ls)[:, :, None] * var[None, None, :]
+        assert np.allclose(got, ref, rtol=1e-12, atol=1e-14)
+    kd = O.kern_Kdiag(kind, torch.tensor(X), O._t(ls), O._t(var)).numpy()
+    assert np.allclose(kd, np.einsum("iir->ir", O.kern_K(kind, torch.tensor(X), None, torch.tensor(ls),
+                                                         torch.tensor(var)).numpy()), rtol=1e-12)
+    chol = O.kern_cholesky(kind, torch.tensor(X), O._t(ls), O._t(var)).numpy()
+    K = O.kern_K(kind, torch.tensor(X), None, O._t(ls), O._t(var)).numpy()
+    for i in range(3):
+        assert np.allclose(K[:, :, i], chol[:, :, i] @ chol[:, :, i].T, atol=1e-4)
+
+
+def test_kronecker_and_rbf2d():
+    # testing/test_kronecker.py:21-54
+    rng = np.random.RandomState(0)
+    A, B = rng.randn(3, 2), rng.randn(5, 4)
+    assert np.allclose(O.kronecker_product(torch.tensor(A), torch.tensor(B)).numpy(), O.loop_kronecker(A, B))
+    X1, X2 = rng.randn(3), rng.randn(5)
+    X = np.array([[a, b] for a in X1 for b in X2])
+    chol = O.rbf2d_cholesky(torch.tensor(X1[:, None]), torch.tensor(X2[:, None]), O._t([1.0]),
+                            O._t([1.0])).numpy()[:, :, 0]
+    K = O.kcore("rbf", O._t(X), None, O._t([1.0])).numpy()
+    assert np.allclose(K, chol @ chol.T, atol=1e-4)
+
+
+def test_los_matrix_matches_loops_and_quirks():
+    r, z = np.linspace(0, 1, 30), np.linspace(-0.9, 0.9, 40)
+    A = O.make_los_matrix(r, z)
+    assert np.array_equal(A, O.make_los_matrix_loops(r, z))
+    assert np.all(A[:, 0] == 0.0)
+    assert abs((A != 0).mean() - 0.555) < 1e-3 and abs(A.max() - 0.4202) < 1e-3
+    c = O.make_cos_theta(r, z)
+    assert c.shape == (40, 30) and np.all(np.abs(c) <= 1.0)
+
+
+def test_literal_and_gemm_form_sampling_agree():
+    rng = np.random.RandomState(5)
+    n, R, S = 12, 2, 4
+    args = [torch.tensor(rng.randn(n, R)), torch.tensor(rng.randn(n, n, R)),
+            torch.tensor(rng.randn(n, n, R)), torch.tensor(rng.randn(n, R)), torch.tensor(rng.randn(R, S, n))]
+    f1, k1 = O.stvgp_sample(*args)
+    f2, k2 = O.stvgp_sample_literal(*args)
+    assert torch.allclose(f1, f2, rtol=1e-12, atol=1e-12) and abs(float(k1 - k2)) < 1e-10
+
+
+def test_G5_mc_kl_converges_to_analytic():
+    rng = np.random.RandomState(6)
+    n, S = 8, 200000
+    q_mu = torch.tensor(0.3 * rng.randn(n, 1))
+    q_sqrt = torch.tensor((0.5 * np.eye(n) + 0.1 * np.tril(rng.randn(n, n)))[:, :, None])
+    L = torch.eye(n, dtype=O.DT)[:, :, None]
+    eps = torch.tensor(rng.randn(1, S, n))
+    _, KL = O.stvgp_sample(q_mu, q_sqrt, L, torch.zeros(n, 1, dtype=O.DT), eps)
+    assert abs(float(KL) / S - float(O.gauss_kl_white(q_mu, q_sqrt))) < 0.02
+
+
+def test_gradient_against_finite_differences():
+    from tests.helpers import abel_data
+    r, z, A, y = abel_data(12, 9)
+    spec = dict(model="stvgp", X=r[:, None], Y=y[:, None],
+                kern=dict(type="rbf_csym", input_dim=1, output_dim=1, ARD=False),
+                mean=dict(type="constant", output_dim=1), lik=dict(type="abel", A=A), num_latent=1)
+    rng = np.random.RandomState(1)
+    x = 0.3 * rng.randn(O.state_size(spec))
+    x[-144:] += np.eye(12).ravel()
+    eps = rng.randn(1, 5, 12)
+    f, g = O.objective(spec, x, eps)
+    for i in (0, 1, 2, 3, 7, 20, 40):
+        h = 1e-6
+        xp, xm = x.copy(), x.copy()
+        xp[i] += h
+        xm[i] -= h
+        fd = (O.objective(spec, xp, eps)[0] - O.objective(spec, xm, eps)[0]) / (2 * h)
+        assert abs(fd - g[i]) < 1e-5 * max(1.0, abs(g[i]))
+
+
+def test_golden_fixtures_are_reproduced():
+    import glob
+    import os
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    assert files, "run tests/golden/make_golden.py"
+    from tests.golden.make_golden import CASES, build_spec
+    for f in files:
+        d = np.load(f, allow_pickle=False)
+        name = os.path.splitext(os.path.basename(f))[0]
+        spec = build_spec(name)
+        fv, g = O.objective(spec, d["x"], d["eps"] if "eps" in d.files else None)
+        assert abs(fv - float(d["f"])) <= 1e-12 * abs(float(d["f"]))
+        assert np.linalg.norm(g - d["g"]) <= 1e-10 * np.linalg.norm(d["g"])
