@@ -185,7 +185,9 @@ def main():
     set_default_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev,
+                                timeout=datetime.timedelta(seconds=180))
 
     n, M, S = CONFIGS[args.config]
     W = max(args.warmup, 3)
@@ -277,6 +279,26 @@ def main():
                 "whole_eval_achieved": work_flops(n, M, S, world) / t_dev * K / 1e12,
                 "whole_eval_frac": work_flops(n, M, S, world) / t_dev * K / 1e12 / peak}
 
+    # kernel launches of one evaluation, counted with torch's CUDA profiler.  The evaluation
+    # contains the all-reduce, so EVERY rank runs it; rank 0 reports.
+    launches = None
+    launch_detail = {}
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            m._objective_device(x, eps=eps)
+            torch.cuda.synchronize()
+        ev = [e for e in prof.events() if e.device_type.name == "CUDA"]
+        mine = [e for e in ev if any(s_ in e.name for s_ in (
+            "gemm_dmma", "panel_kernel", "trsm_", "trtri", "kbuild", "kprep", "tril_", "sumsq", "colsum",
+            "diag_", "kl_finish", "zero_upper", "mirror", "scale_diag", "leaf_rev", "symmetrize", "udiag",
+            "gauss_", "set_identity", "spec_", "skinny_"))]
+        launches = len(mine) * K
+        launch_detail = {"gpinv_b200": len(mine), "all_cuda_kernels": len(ev)}
+    except Exception as e:  # pragma: no cover
+        launch_detail = {"error": repr(e)[:100]}
+    barrier()
+
     if rank == 0:
         nbytes = 8 * x_host.size
         line = {
@@ -286,29 +308,13 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(n, M, S), "parallelism": "mc-samples sharded x%d, replicated Cholesky, 1 all-reduce" % world,
                        "l2": "working set ~1 GB per evaluation exceeds the 126 MB L2; no explicit flush",
-                       "neg_elbo": fval},
+                       "neg_elbo": fval, "launches_per_eval": launch_detail},
             "e2e": {"value": 1.0 / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": nbytes + 8},
-            "gpu_launches": None,
+            "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": roof,
         }
-        # kernel launches inside the timed region: counted with the CUDA profiler API of torch
-        try:
-            from torch.profiler import profile, ProfilerActivity
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                m._objective_device(x, eps=eps)
-                torch.cuda.synchronize()
-            mine = [e for e in prof.events() if e.device_type.name == "CUDA" and
-                    any(s in e.name for s in ("gemm_dmma", "panel_kernel", "trsm_", "trtri", "kbuild", "kprep",
-                                              "tril_", "sumsq", "colsum", "diag_", "kl_finish", "zero_upper",
-                                              "mirror", "scale_diag", "leaf_rev", "symmetrize", "udiag", "gauss_",
-                                              "set_identity"))]
-            line["gpu_launches"] = len(mine) * K
-            line["config"]["launches_per_eval"] = {"gpinv_b200": len(mine),
-                                                   "all_cuda_kernels": len([e for e in prof.events() if e.device_type.name == "CUDA"])}
-        except Exception as e:  # pragma: no cover
-            line["config"]["launch_count_error"] = repr(e)[:100]
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(n, M, S)
         print(json.dumps(line))

@@ -58,6 +58,26 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return v;
 }
 
+// 1/sqrt(v): SFU single-precision seed + two Newton steps in fp64 (<= ~1 ulp for v inside the
+// float range; falls back to the library routine outside it, and for v <= 0 returns NaN/inf like
+// rsqrt()).  About half the latency of rsqrt(double) on the Cholesky pivot chain.
+__device__ __forceinline__ double fast_rsqrt(double v) {
+  if (!(v > 1e-30 && v < 1e30)) return rsqrt(v);
+  double y = (double)rsqrtf((float)v);
+  double t = v * y;
+  double e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  t = v * y;
+  e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  return y;
+}
+// sqrt(v) from y ~ 1/sqrt(v) with one correction step
+__device__ __forceinline__ double sqrt_from_rsqrt(double v, double y) {
+  double l = v * y;
+  return fma(fma(-l, l, v), 0.5 * y, l);
+}
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -264,53 +264,71 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = m0 + wm * 64 + i * 8 + g;
+    // phase 1: issue every global read of this row group back to back (8 loads in flight per
+    // operand) so the epilogue of small-K GEMMs is not a chain of exposed L2 latencies
+    bool ok[4][2], upper[4][2];
+    double cin[4][2], mulv[4][2], wv[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = n0 + wn * 32 + j * 8 + 2 * t + e;
+        bool o = (row < p.M) && (c < p.N);
+        upper[j][e] = false;
+        if (EF & EF_LOWER) {
+          upper[j][e] = o && (c > row);
+          o = o && (c <= row);
+        }
+        ok[j][e] = o;
+        cin[j][e] = 0.0; mulv[j][e] = 1.0; wv[j][e] = 0.0;
+        if (o) {
+          if ((EF & EF_BETA) && beta != 0.0) cin[j][e] = p.Cin[(size_t)row * p.ldcin + c];
+          if (EF & EF_MULMAT) mulv[j][e] = __ldg(p.mul + (size_t)row * p.ldmul + c);
+          if (EF & EF_DOT) wv[j][e] = __ldg(p.W + (size_t)row * p.ldw + c);
+        }
+      }
+    }
+    // phase 2: combine, reduce, store
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = n0 + wn * 32 + j * 8 + 2 * t;
       double v[2];
-      bool ok[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int c = col + e;
-        ok[e] = (row < p.M) && (c < p.N);
-        bool upper = false;
-        if (EF & EF_LOWER) {
-          upper = ok[e] && (c > row);
-          ok[e] = ok[e] && (c <= row);
-        }
         double x = alpha * acc[i][j][e];
-        if (ok[e]) {
-          if (EF & EF_DOT) r_dot += x * __ldg(p.W + (size_t)row * p.ldw + c);
-          if (EF & EF_MULMAT) x *= __ldg(p.mul + (size_t)row * p.ldmul + c);
-          if ((EF & EF_BETA) && beta != 0.0) x += beta * p.Cin[(size_t)row * p.ldcin + c];
+        if (ok[j][e]) {
+          if (EF & EF_DOT) r_dot += x * wv[j][e];
+          if (EF & EF_MULMAT) x *= mulv[j][e];
+          if (EF & EF_BETA) x += beta * cin[j][e];
           if (EF & EF_COLVEC) x += __ldg(p.colvec + c);
           if (EF & EF_SUMSQ) r_sumsq += x * x;
           if (EF & EF_COLSUM) r_col[j][e] += x;
         }
         v[e] = x;
         // strict upper part of a diagonal tile: store exact zeros so the result is a clean tril()
-        if ((EF & EF_LOWER) && !(EF & EF_ATOMIC) && upper && p.out) {
+        if ((EF & EF_LOWER) && !(EF & EF_ATOMIC) && upper[j][e] && p.out) {
           v[e] = 0.0;
           p.out[(size_t)row * p.ldo + c] = 0.0;
         }
       }
       if (EF & EF_ATOMIC) {
-        if (ok[0]) atomicAdd(p.out + (size_t)row * p.ldo + col, v[0]);
-        if (ok[1]) atomicAdd(p.out + (size_t)row * p.ldo + col + 1, v[1]);
+        if (ok[j][0]) atomicAdd(p.out + (size_t)row * p.ldo + col, v[0]);
+        if (ok[j][1]) atomicAdd(p.out + (size_t)row * p.ldo + col + 1, v[1]);
       } else {
         if (p.out) {
           double* o = p.out + (size_t)row * p.ldo + col;
-          if (ok[0] && ok[1] && p.vecO) {
+          if (ok[j][0] && ok[j][1] && p.vecO) {
             *reinterpret_cast<double2*>(o) = make_double2(v[0], v[1]);
           } else {
-            if (ok[0]) o[0] = v[0];
-            if (ok[1]) o[1] = v[1];
+            if (ok[j][0]) o[0] = v[0];
+            if (ok[j][1]) o[1] = v[1];
           }
         }
         if (EF & EF_EXP2) {
           double* o = p.out2 + (size_t)row * p.ldo2 + col;
-          if (ok[0]) o[0] = exp(v[0]);
-          if (ok[1]) o[1] = exp(v[1]);
+          if (ok[j][0]) o[0] = exp(v[0]);
+          if (ok[j][1]) o[1] = exp(v[1]);
         }
       }
     }

@@ -46,18 +46,19 @@ __global__ void __launch_bounds__(pcfg::NB + pcfg::RB) panel_kernel(double* __re
   const int row_base = i0 + b + blockIdx.x * RB;
   const int nrows = max(0, min(RB, n - row_base));
 
+  // asynchronous 8-byte copies: all 64 loads of a thread are in flight at once
   for (int idx = tid; idx < NB * NB; idx += nthr) {
     const int r = idx >> 6, c = idx & 63;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < b && c < b) v = A[(size_t)(i0 + r) * lda + i0 + c];
-    Rs[r * LDR + c] = v;
+    if (r < b && c < b) cp_async8(Rs + r * LDR + c, A + (size_t)(i0 + r) * lda + i0 + c, 8);
+    else Rs[r * LDR + c] = (r == c) ? 1.0 : 0.0;
   }
   for (int idx = tid; idx < RB * NB; idx += nthr) {
     const int r = idx >> 6, c = idx & 63;
-    double v = 0.0;
-    if (r < nrows && c < b) v = A[(size_t)(row_base + r) * lda + i0 + c];
-    Rs[(NB + r) * LDR + c] = v;
+    if (r < nrows && c < b) cp_async8(Rs + (NB + r) * LDR + c, A + (size_t)(row_base + r) * lda + i0 + c, 8);
+    else Rs[(NB + r) * LDR + c] = 0.0;
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
 
   int fail = INT_MAX;
@@ -83,32 +84,36 @@ __global__ void __launch_bounds__(pcfg::NB + pcfg::RB) panel_kernel(double* __re
       for (int q = 0; q < 8; ++q) Ds[(tid - c0) * 9 + q] = s[q];
     }
     __syncthreads();
-    // every thread factors the 8x8 diagonal block redundantly in registers
+    // every thread factors the 8x8 diagonal block redundantly in registers, right-looking so
+    // the dependent chain per pivot is rsqrt -> scale -> one FMA
     double l[8][8], inv[8];
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
-      for (int bb = 0; bb <= a; ++bb) {
-        double v = Ds[a * 9 + bb];
+      for (int bb = 0; bb <= a; ++bb) l[a][bb] = Ds[a * 9 + bb];
 #pragma unroll
-        for (int m = 0; m < bb; ++m) v -= l[a][m] * l[bb][m];
-        if (a == bb) {
-          if (!(v > 0.0)) fail = min(fail, c0 + a);
-          l[a][a] = sqrt(v);
-          inv[a] = rsqrt(v);   // independent of the sqrt: shortens the pivot chain
-        } else {
-          l[a][bb] = v * inv[bb];
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      const double v = l[j][j];
+      if (!(v > 0.0)) fail = min(fail, c0 + j);
+      const double y = fast_rsqrt(v);
+      inv[j] = y;
+#pragma unroll
+      for (int i = j + 1; i < 8; ++i) l[i][j] *= y;
+#pragma unroll
+      for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+        for (int k = j + 1; k <= i; ++k) l[i][k] -= l[i][j] * l[k][j];
+      l[j][j] = sqrt_from_rsqrt(v, y);
     }
     if (active) {
       double x[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        double v = s[q];
+      for (int q = 0; q < 8; ++q) x[q] = s[q];
 #pragma unroll
-        for (int m = 0; m < q; ++m) v -= x[m] * l[q][m];
-        x[q] = v * inv[q];
+      for (int q = 0; q < 8; ++q) {
+        x[q] *= inv[q];
+#pragma unroll
+        for (int m = q + 1; m < 8; ++m) x[m] -= x[q] * l[m][q];
       }
       if (tid < c0 + 8) {  // rows of the diagonal 8x8 block: exact diagonal, zero upper part
         const int a = tid - c0;
