@@ -2,37 +2,63 @@
 #include "gemm.cuh"
 
 #include <cstdio>
-#include <mutex>
 
 namespace gpinv {
 
 namespace {
 
-template <int LA, int LB, unsigned EF>
+template <class Cfg, int LA, int LB, unsigned EF>
 int launch_inst(const GemmParams& p, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kern = gemm_dmma_kernel<LA, LB, EF>;
+  auto kern = gemm_dmma_kernel<Cfg, LA, LB, EF>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         gemm_cfg::SMEM_BYTES);
+                                         Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_last_error(cudaGetErrorString(e));
       return GPINV_ERR_CUDA;
     }
     attr_set = true;
   }
-  kern<<<grid, gemm_cfg::THREADS, gemm_cfg::SMEM_BYTES, stream>>>(p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+inline int tiles_of(int M, int N, int bm, bool lower) {
+  const int tm = cdiv(M, bm), tn = cdiv(N, bm);
+  return lower ? tm * (tm + 1) / 2 : tm * tn;
+}
+
+// Small tiles when the big-tile grid cannot fill the machine or K is too short to amortise a
+// 128x128 tile's fill / epilogue.
+inline bool use_small(const GemmParams& p, bool lower) {
+  if (p.force_cfg == 1) return false;
+  if (p.force_cfg == 2) return true;
+  const int batch = p.batch > 1 ? p.batch : 1;
+  const long long big_tiles = (long long)tiles_of(p.M, p.N, 128, lower) * batch * (p.splitk > 1 ? p.splitk : 1);
+  if (big_tiles < 120) return true;
+  if (p.K <= 128 && big_tiles < 600) return true;
+  return false;
+}
+
+template <class Cfg>
+int dispatch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream);
+
 }  // namespace
+
+int gemm_tile_count(int M, int N, int K, bool lower, int batch) {
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K; p.batch = batch; p.splitk = 1;
+  const int bm = use_small(p, lower) ? 64 : 128;
+  return tiles_of(M, N, bm, lower) * (batch > 1 ? batch : 1);
+}
 
 #define GPINV_GEMM_CASE(LA_, LB_, EF_)                                   \
   if (la == (LA_) && lb == (LB_) && ef == (unsigned)(EF_))               \
-    return launch_inst<LA_, LB_, (unsigned)(EF_)>(p, grid, stream);
+    return launch_inst<Cfg, LA_, LB_, (unsigned)(EF_)>(p, grid, stream);
 
 #define GPINV_GEMM_GENERIC(LA_, LB_)                      \
   GPINV_GEMM_CASE(LA_, LB_, EF_BETA)                      \
@@ -40,30 +66,16 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
   GPINV_GEMM_CASE(LA_, LB_, EF_ATOMIC)                    \
   GPINV_GEMM_CASE(LA_, LB_, EF_ATOMIC | EF_LOWER)
 
-int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) {
-  using namespace gemm_cfg;
-  if (p.M <= 0 || p.N <= 0) return GPINV_OK;
-  if (p.splitk < 1) p.splitk = 1;
-  if (p.splitk > 1 && !(ef & EF_ATOMIC)) {
-    set_last_error("gemm: split-K requires the atomic epilogue");
-    return GPINV_ERR_ARG;
-  }
-  p.tiles_m = cdiv(p.M, BM);
-  p.tiles_n = cdiv(p.N, BN);
+namespace {
+template <class Cfg>
+int dispatch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) {
+  p.tiles_m = cdiv(p.M, Cfg::BM);
+  p.tiles_n = cdiv(p.N, Cfg::BN);
   if ((ef & EF_LOWER) && p.tiles_m != p.tiles_n) {
     set_last_error("gemm: lower-triangular output must be square");
     return GPINV_ERR_ARG;
   }
-  p.vecA = aligned16(p.A) && (p.lda % 2 == 0);
-  p.vecB = aligned16(p.B) && (p.ldb % 2 == 0);
-  p.vecO = (p.out == nullptr) || (aligned16(p.out) && (p.ldo % 2 == 0));
   const int ntiles = (ef & EF_LOWER) ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
-  if (p.batch < 1) p.batch = 1;
-  if (p.batch > 1) {
-    p.vecA = p.vecA && (p.strideA % 2 == 0);
-    p.vecB = p.vecB && (p.strideB % 2 == 0);
-    p.vecO = p.vecO && (p.strideO % 2 == 0);
-  }
   dim3 grid(ntiles, p.splitk, p.batch);
 
   GPINV_GEMM_GENERIC(LK, LK)
@@ -80,6 +92,27 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
   GPINV_GEMM_CASE(LMN, LMN, EF_LOWER | EF_BETA | EF_DOT)      // Lbar += tril(Fbar^T U), <.,Lc>
   set_last_error("gemm: no kernel instantiated for this layout / epilogue combination");
   return GPINV_ERR_ARG;
+}
+}  // namespace
+
+int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) {
+  if (p.M <= 0 || p.N <= 0) return GPINV_OK;
+  if (p.splitk < 1) p.splitk = 1;
+  if (p.splitk > 1 && !(ef & EF_ATOMIC)) {
+    set_last_error("gemm: split-K requires the atomic epilogue");
+    return GPINV_ERR_ARG;
+  }
+  p.vecA = aligned16(p.A) && (p.lda % 2 == 0);
+  p.vecB = aligned16(p.B) && (p.ldb % 2 == 0);
+  p.vecO = (p.out == nullptr) || (aligned16(p.out) && (p.ldo % 2 == 0));
+  if (p.batch < 1) p.batch = 1;
+  if (p.batch > 1) {
+    p.vecA = p.vecA && (p.strideA % 2 == 0);
+    p.vecB = p.vecB && (p.strideB % 2 == 0);
+    p.vecO = p.vecO && (p.strideO % 2 == 0);
+  }
+  if (use_small(p, (ef & EF_LOWER) != 0)) return dispatch<CfgSmall>(la, lb, ef, p, stream);
+  return dispatch<CfgBig>(la, lb, ef, p, stream);
 }
 
 int gemm_simple(int la, int lb, int M, int N, int K, double alpha, const double* A, int lda,

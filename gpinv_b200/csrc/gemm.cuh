@@ -9,8 +9,10 @@
 //                   LMN : element (r,k) at p[k*ld + r]   (row index contiguous)
 // so BLAS "C = A B^T" is <LK,LK>, "C = A B" is <LK,LMN>, "C = A^T B" is <LMN,LMN>.
 //
-// CTA tile 128x128x16, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA tiles, accumulators in
-// registers (128 regs), 4-stage cp.async (LDGSTS) pipeline, padded conflict-free smem.
+// Two tile configurations: CfgBig = CTA tile 128x128x16, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA
+// tiles, accumulators in registers (128 regs), 4-stage cp.async (LDGSTS) pipeline, 1 CTA/SM;
+// CfgSmall = 64x64x16, 4 warps, 3 stages, 3 CTAs/SM for small or short-K problems where one
+// 128x128 tile is a whole SM's worth of serial work.  Padded conflict-free smem in both.
 #pragma once
 #include "common.cuh"
 
@@ -56,32 +58,43 @@ struct GemmParams {
   int kmode;   // 0 full | 1: k < n0+BN | 2: k >= n0 | 3: k < m0+BM | 4: k >= m0 | 5: n0 <= k < m0+BM
   int splitk;  // >= 1
   int tiles_m, tiles_n;
+  int force_cfg;  // 0 auto | 1 big (128x128) | 2 small (64x64)
   int vecA, vecB, vecO;  // 16-byte alignment of operands / output rows
   // batching over blockIdx.z (element strides; 0 = shared operand)
   int batch;
   long long strideA, strideB, strideO, strideCin;
 };
 
-namespace gemm_cfg {
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int THREADS = 256;
-constexpr int STAGES = 4;
-constexpr int LDK = BK + 4;     // LK   tile: [128][20]
-constexpr int LDM = BM + 4;     // LMN  tile: [16][132]
-constexpr int TILE_ELEMS = BM * LDK;  // 2560 doubles >= 16*132 = 2112
-constexpr int STAGE_ELEMS = 2 * TILE_ELEMS;
-constexpr int SMEM_BYTES = STAGES * STAGE_ELEMS * 8;  // 163840
-}  // namespace gemm_cfg
+template <int TM_, int TN_, int WM_, int WN_, int STAGES_, int MINB_>
+struct GemmCfg {
+  static constexpr int TM = TM_, TN = TN_, WM = WM_, WN = WN_;   // DMMA tiles per warp, warps per CTA
+  static constexpr int BM = WM * TM * 8, BN = WN * TN * 8, BK = 16;
+  static constexpr int THREADS = WM * WN * 32;
+  static constexpr int STAGES = STAGES_;
+  static constexpr int MINB = MINB_;
+  static constexpr int LDK = BK + 4;                 // LK  tile: [rows][20]
+  static constexpr int LDMA = BM + 4, LDMB = BN + 4; // LMN tile: [16][rows+4]
+  static constexpr int A_ELEMS = (BM * LDK > BK * LDMA) ? BM * LDK : BK * LDMA;
+  static constexpr int B_ELEMS = (BN * LDK > BK * LDMB) ? BN * LDK : BK * LDMB;
+  static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_ELEMS * 8;
+};
+// 128x128 tile, 8 warps, warp tile 64x32, 4 stages, 160 KB smem, 1 CTA/SM: the throughput config
+using CfgBig = GemmCfg<8, 4, 2, 4, 4, 1>;
+// 64x64 tile, 4 warps, warp tile 32x32, 3 stages, 60 KB smem, 3 CTAs/SM: small / short-K problems
+using CfgSmall = GemmCfg<4, 4, 2, 2, 3, 3>;
 
-template <int LAYOUT>
+template <int LAYOUT, int ROWS, int THREADS>
 __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restrict__ g, int ld,
                                                int r0, int k0, int Rmax, int Kmax, int vec,
                                                int tid) {
-  using namespace gemm_cfg;
+  constexpr int BK = 16;
+  constexpr int LDK = BK + 4;
+  constexpr int LDM = ROWS + 4;
   if (LAYOUT == LK) {
     if (vec) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < ROWS * 8 / THREADS; ++c) {
         const int id = tid + c * THREADS;
         const int row = id >> 3, kc = (id & 7) * 2;
         const int gr = r0 + row, gk = k0 + kc;
@@ -91,7 +104,7 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < ROWS * 16 / THREADS; ++c) {
         const int id = tid + c * THREADS;
         const int row = id >> 4, k = id & 15;
         const int gr = r0 + row, gk = k0 + k;
@@ -103,9 +116,9 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
   } else {
     if (vec) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < ROWS * 8 / THREADS; ++c) {
         const int id = tid + c * THREADS;
-        const int k = id >> 6, rc = (id & 63) * 2;
+        const int k = id / (ROWS / 2), rc = (id % (ROWS / 2)) * 2;
         const int gr = r0 + rc, gk = k0 + k;
         int valid = (gk < Kmax) ? min(max(Rmax - gr, 0), 2) : 0;
         const double* src = valid ? g + (size_t)gk * ld + gr : g;
@@ -113,9 +126,9 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < ROWS * 16 / THREADS; ++c) {
         const int id = tid + c * THREADS;
-        const int k = id >> 7, r = id & 127;
+        const int k = id / ROWS, r = id % ROWS;
         const int gr = r0 + r, gk = k0 + k;
         const bool ok = (gr < Rmax) && (gk < Kmax);
         const double* src = ok ? g + (size_t)gk * ld + gr : g;
@@ -125,9 +138,11 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
   }
 }
 
-template <int LA, int LB, unsigned EF>
-__global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const GemmParams pin) {
-  using namespace gemm_cfg;
+template <class Cfg, int LA, int LB, unsigned EF>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(const GemmParams pin) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
+  constexpr int TM = Cfg::TM, TN = Cfg::TN, LDK = Cfg::LDK, LDMA = Cfg::LDMA, LDMB = Cfg::LDMB;
+  constexpr int A_ELEMS = Cfg::A_ELEMS, STAGE_ELEMS = Cfg::STAGE_ELEMS;
   extern __shared__ __align__(16) double smem[];
   GemmParams p = pin;
   if (p.batch > 1) {
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+  const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
 
   // ---- tile decode (heavy tiles first so the hardware scheduler balances the tail) ----
   int tm, tn;
@@ -192,31 +207,31 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
     if (ktiles == 0) return;
   }
 
-  double acc[8][4][2];
+  double acc[TM][TN][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // ---- pipeline prologue ----
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < ktiles) {
       double* sA = smem + s * STAGE_ELEMS;
-      double* sB = sA + TILE_ELEMS;
-      gemm_load_tile<LA>(sA, p.A, p.lda, m0, kb + s * BK, p.M, ke, p.vecA, tid);
-      gemm_load_tile<LB>(sB, p.B, p.ldb, n0, kb + s * BK, p.N, ke, p.vecB, tid);
+      double* sB = sA + A_ELEMS;
+      gemm_load_tile<LA, BM, THREADS>(sA, p.A, p.lda, m0, kb + s * BK, p.M, ke, p.vecA, tid);
+      gemm_load_tile<LB, BN, THREADS>(sB, p.B, p.ldb, n0, kb + s * BK, p.N, ke, p.vecB, tid);
     }
     cp_async_commit();
   }
 
   // fragment base offsets inside a tile
-  const int aoff = (LA == LK) ? ((wm * 64 + g) * LDK + t) : (t * LDM + wm * 64 + g);
-  const int boff = (LB == LK) ? ((wn * 32 + g) * LDK + t) : (t * LDM + wn * 32 + g);
+  const int aoff = (LA == LK) ? ((wm * TM * 8 + g) * LDK + t) : (t * LDMA + wm * TM * 8 + g);
+  const int boff = (LB == LK) ? ((wn * TN * 8 + g) * LDK + t) : (t * LDMB + wn * TN * 8 + g);
   constexpr int A_ISTRIDE = (LA == LK) ? 8 * LDK : 8;   // next 8-row DMMA tile
-  constexpr int A_KSTRIDE = (LA == LK) ? 4 : 4 * LDM;   // next k4 step
+  constexpr int A_KSTRIDE = (LA == LK) ? 4 : 4 * LDMA;  // next k4 step
   constexpr int B_JSTRIDE = (LB == LK) ? 8 * LDK : 8;
-  constexpr int B_KSTRIDE = (LB == LK) ? 4 : 4 * LDM;
+  constexpr int B_KSTRIDE = (LB == LK) ? 4 : 4 * LDMB;
 
   for (int kt = 0; kt < ktiles; ++kt) {
     cp_async_wait<STAGES - 2>();
@@ -225,25 +240,25 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
       const int nk = kt + STAGES - 1;
       if (nk < ktiles) {
         double* sA = smem + (nk % STAGES) * STAGE_ELEMS;
-        double* sB = sA + TILE_ELEMS;
-        gemm_load_tile<LA>(sA, p.A, p.lda, m0, kb + nk * BK, p.M, ke, p.vecA, tid);
-        gemm_load_tile<LB>(sB, p.B, p.ldb, n0, kb + nk * BK, p.N, ke, p.vecB, tid);
+        double* sB = sA + A_ELEMS;
+        gemm_load_tile<LA, BM, THREADS>(sA, p.A, p.lda, m0, kb + nk * BK, p.M, ke, p.vecA, tid);
+        gemm_load_tile<LB, BN, THREADS>(sB, p.B, p.ldb, n0, kb + nk * BK, p.N, ke, p.vecB, tid);
       }
       cp_async_commit();
     }
     const double* sA = smem + (kt % STAGES) * STAGE_ELEMS + aoff;
-    const double* sB = smem + (kt % STAGES) * STAGE_ELEMS + TILE_ELEMS + boff;
+    const double* sB = smem + (kt % STAGES) * STAGE_ELEMS + A_ELEMS + boff;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[8], b[4];
+      double a[TM], b[TN];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = sA[i * A_ISTRIDE + kk * A_KSTRIDE];
+      for (int i = 0; i < TM; ++i) a[i] = sA[i * A_ISTRIDE + kk * A_KSTRIDE];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sB[j * B_JSTRIDE + kk * B_KSTRIDE];
+      for (int j = 0; j < TN; ++j) b[j] = sB[j * B_JSTRIDE + kk * B_KSTRIDE];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
   cp_async_wait<0>();
@@ -257,22 +272,22 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
     if (p.beta_dev) beta *= __ldg(p.beta_dev);
   }
   double r_sumsq = 0.0, r_dot = 0.0;
-  double r_col[4][2];
+  double r_col[TN][2];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) r_col[j][0] = r_col[j][1] = 0.0;
+  for (int j = 0; j < TN; ++j) r_col[j][0] = r_col[j][1] = 0.0;
 
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = m0 + wm * 64 + i * 8 + g;
+  for (int i = 0; i < TM; ++i) {
+    const int row = m0 + wm * TM * 8 + i * 8 + g;
     // phase 1: issue every global read of this row group back to back (8 loads in flight per
     // operand) so the epilogue of small-K GEMMs is not a chain of exposed L2 latencies
-    bool ok[4][2], upper[4][2];
-    double cin[4][2], mulv[4][2], wv[4][2];
+    bool ok[TN][2], upper[TN][2];
+    double cin[TN][2], mulv[TN][2], wv[TN][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < TN; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int c = n0 + wn * 32 + j * 8 + 2 * t + e;
+        const int c = n0 + wn * TN * 8 + j * 8 + 2 * t + e;
         bool o = (row < p.M) && (c < p.N);
         upper[j][e] = false;
         if (EF & EF_LOWER) {
@@ -290,8 +305,8 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
     }
     // phase 2: combine, reduce, store
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = n0 + wn * 32 + j * 8 + 2 * t;
+    for (int j = 0; j < TN; ++j) {
+      const int col = n0 + wn * TN * 8 + j * 8 + 2 * t;
       double v[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -343,18 +358,21 @@ __global__ void __launch_bounds__(gemm_cfg::THREADS, 1) gemm_dmma_kernel(const G
   }
   if (EF & EF_COLSUM) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < TN; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         double s = r_col[j][e];
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         s += __shfl_xor_sync(0xffffffffu, s, 8);
         s += __shfl_xor_sync(0xffffffffu, s, 16);
-        const int c = n0 + wn * 32 + j * 8 + 2 * t + e;
+        const int c = n0 + wn * TN * 8 + j * 8 + 2 * t + e;
         if (g == 0 && c < p.N) atomicAdd(p.colsum + c, s);
       }
   }
 }
+
+// Number of CTA tiles the launcher will use for an M x N problem (for split-K heuristics).
+int gemm_tile_count(int M, int N, int K, bool lower, int batch);
 
 // Host-side launcher (defined in gemm.cu).  `la`,`lb` are Layout values, `ef` the flag set.
 int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream);

@@ -324,9 +324,8 @@ static int set_smem_attrs() {
 }
 
 static int pick_splitk(int M, int N, int K, bool lower) {
-  const int tm = cdiv(M, gemm_cfg::BM), tn = cdiv(N, gemm_cfg::BN);
-  const int tiles = lower ? tm * (tm + 1) / 2 : tm * tn;
-  const int ktiles = cdiv(K, gemm_cfg::BK);
+  const int tiles = gemm_tile_count(M, N, K, lower, 1);
+  const int ktiles = cdiv(K, 16);
   int s = 148 / (tiles > 0 ? tiles : 1);
   s = min(s, ktiles / 8);   // keep >= 8 k-tiles (128 columns of K) per split
   return max(s, 1);
