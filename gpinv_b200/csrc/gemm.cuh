@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(cons
         ok[j][e] = o;
         cin[j][e] = 0.0; mulv[j][e] = 1.0; wv[j][e] = 0.0;
         if (o) {
-          if ((EF & EF_BETA) && beta != 0.0) cin[j][e] = p.Cin[(size_t)row * p.ldcin + c];
+          if ((EF & EF_BETA) && beta != 0.0) cin[j][e] = __ldcg(p.Cin + (size_t)row * p.ldcin + c);
           if (EF & EF_MULMAT) mulv[j][e] = __ldg(p.mul + (size_t)row * p.ldmul + c);
           if (EF & EF_DOT) wv[j][e] = __ldg(p.W + (size_t)row * p.ldw + c);
         }

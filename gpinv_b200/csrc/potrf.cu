@@ -12,6 +12,7 @@
 // Replaces tf.cholesky + its CholeskyGrad op at GPinv/kernels.py:59 and
 // GPinv/kronecker.py:54,57 (reference /root/reference).
 #include <climits>
+#include <cstdlib>
 
 #include "gemm.cuh"
 
@@ -46,20 +47,48 @@ __global__ void __launch_bounds__(pcfg::NB + pcfg::RB) panel_kernel(double* __re
   const int row_base = i0 + b + blockIdx.x * RB;
   const int nrows = max(0, min(RB, n - row_base));
 
-  // asynchronous 8-byte copies: all 64 loads of a thread are in flight at once
-  for (int idx = tid; idx < NB * NB; idx += nthr) {
-    const int r = idx >> 6, c = idx & 63;
-    if (r < b && c < b) cp_async8(Rs + r * LDR + c, A + (size_t)(i0 + r) * lda + i0 + c, 8);
-    else Rs[r * LDR + c] = (r == c) ? 1.0 : 0.0;
+  // L2-only (ld.global.cg) loads, 8 in flight per thread: the look-ahead runs this kernel
+  // concurrently with the side-stream trailing update, so L1 must not be trusted.
+  for (int base = 0; base < NB * NB; base += 8 * nthr) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * nthr + tid;
+      const int r = idx >> 6, c = idx & 63;
+      v[u] = (r == c) ? 1.0 : 0.0;
+      if (idx < NB * NB && r < b && c < b) v[u] = __ldcg(A + (size_t)(i0 + r) * lda + i0 + c);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * nthr + tid;
+      if (idx < NB * NB) Rs[(idx >> 6) * LDR + (idx & 63)] = v[u];
+    }
   }
-  for (int idx = tid; idx < RB * NB; idx += nthr) {
-    const int r = idx >> 6, c = idx & 63;
-    if (r < nrows && c < b) cp_async8(Rs + (NB + r) * LDR + c, A + (size_t)(row_base + r) * lda + i0 + c, 8);
-    else Rs[(NB + r) * LDR + c] = 0.0;
+  for (int base = 0; base < RB * NB; base += 8 * nthr) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * nthr + tid;
+      const int r = idx >> 6, c = idx & 63;
+      v[u] = 0.0;
+      if (idx < RB * NB && r < nrows && c < b) v[u] = __ldcg(A + (size_t)(row_base + r) * lda + i0 + c);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * nthr + tid;
+      if (idx < RB * NB) Rs[(NB + (idx >> 6)) * LDR + (idx & 63)] = v[u];
+    }
   }
-  cp_async_commit();
-  cp_async_wait<0>();
   __syncthreads();
+  // Ticket: the diagonal block is overwritten in place, so only the CTA that is LAST to have
+  // loaded it may write the factor back (CTAs can start arbitrarily late when another stream
+  // shares the GPU).  info[1] is the ticket counter; the last CTA resets it.
+  __shared__ int s_last;
+  if (tid == 0) {
+    const int ticket = atomicAdd(info + 1, 1);
+    s_last = (ticket == (int)gridDim.x - 1);
+    if (s_last) info[1] = 0;
+  }
 
   int fail = INT_MAX;
   double* myrow = Rs + tid * LDR;
@@ -133,7 +162,7 @@ __global__ void __launch_bounds__(pcfg::NB + pcfg::RB) panel_kernel(double* __re
     __syncthreads();
   }
 
-  if (blockIdx.x == 0) {
+  if (s_last) {   // (s_last was written before the first barrier of the main loop)
     for (int idx = tid; idx < NB * NB; idx += nthr) {
       const int r = idx >> 6, c = idx & 63;
       if (r < b && c < b) A[(size_t)(i0 + r) * lda + i0 + c] = (c <= r) ? Rs[r * LDR + c] : 0.0;
@@ -331,11 +360,38 @@ static int pick_splitk(int M, int N, int K, bool lower) {
   return max(s, 1);
 }
 
+// Side stream + events for the look-ahead (one set per device, created on first use).
+struct LookAhead {
+  cudaStream_t side = nullptr;
+  cudaEvent_t evP = nullptr, evB = nullptr;
+  bool ok = false;
+};
+static LookAhead* lookahead_for_current_device() {
+  static LookAhead table[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  LookAhead& la = table[dev];
+  if (!la.ok) {
+    if (cudaStreamCreateWithFlags(&la.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&la.evP, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&la.evB, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    la.ok = true;
+  }
+  return &la;
+}
+
+// Two-level right-looking Cholesky with look-ahead: after outer panel o is factored, the
+// trailing update is split into (a) the columns of the NEXT outer panel, done on the caller's
+// stream so panel o+1 can start at once, and (b) the rest of the trailing matrix, done on a side
+// stream concurrently with (a) and with the factorisation of panel o+1.
 int potrf_f64(double* A, int n, int lda, int* info, cudaStream_t st) {
   using namespace pcfg;
   int rc = set_smem_attrs();
   if (rc) return rc;
-  if (cudaMemsetAsync(info, 0, sizeof(int), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  if (cudaMemsetAsync(info, 0, 2 * sizeof(int), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  static const bool no_la = (getenv("GPINV_NO_LOOKAHEAD") != nullptr);
+  LookAhead* la = (n > 2 * NBO && !no_la) ? lookahead_for_current_device() : nullptr;
+  bool side_pending = false;
   for (int o = 0; o < n; o += NBO) {
     const int w = min(NBO, n - o);
     for (int i = o; i < o + w; i += NB) {
@@ -350,13 +406,35 @@ int potrf_f64(double* A, int n, int lda, int* info, cudaStream_t st) {
         if (rc) return rc;
       }
     }
-    if (o + w < n) {
-      double* P = A + (size_t)(o + w) * lda + o;
-      rc = gemm_simple(LK, LK, n - o - w, n - o - w, w, -1.0, P, lda, P, lda, 1.0,
-                       A + (size_t)(o + w) * lda + (o + w), lda, true, 0, 1, st);
+    const int t0 = o + w;   // first trailing row / column
+    if (t0 >= n) break;
+    double* P = A + (size_t)t0 * lda + o;
+    if (!la) {
+      rc = gemm_simple(LK, LK, n - t0, n - t0, w, -1.0, P, lda, P, lda, 1.0,
+                       A + (size_t)t0 * lda + t0, lda, true, 0, 1, st);
       if (rc) return rc;
+      continue;
+    }
+    const int nw = min(NBO, n - t0);   // width of the next outer panel
+    const int t1 = t0 + nw;
+    if (cudaEventRecord(la->evP, st) != cudaSuccess) return GPINV_ERR_CUDA;
+    if (cudaStreamWaitEvent(la->side, la->evP, 0) != cudaSuccess) return GPINV_ERR_CUDA;
+    if (side_pending && cudaStreamWaitEvent(st, la->evB, 0) != cudaSuccess) return GPINV_ERR_CUDA;
+    // (a) next panel's columns, all trailing rows (the upper part of its diagonal block is junk)
+    rc = gemm_simple(LK, LK, n - t0, nw, w, -1.0, P, lda, P, lda, 1.0, A + (size_t)t0 * lda + t0,
+                     lda, false, 0, 1, st);
+    if (rc) return rc;
+    side_pending = false;
+    if (t1 < n) {  // (b) the rest, lower triangle, on the side stream
+      double* P1 = A + (size_t)t1 * lda + o;
+      rc = gemm_simple(LK, LK, n - t1, n - t1, w, -1.0, P1, lda, P1, lda, 1.0,
+                       A + (size_t)t1 * lda + t1, lda, true, 0, 1, la->side);
+      if (rc) return rc;
+      if (cudaEventRecord(la->evB, la->side) != cudaSuccess) return GPINV_ERR_CUDA;
+      side_pending = true;
     }
   }
+  if (side_pending && cudaStreamWaitEvent(st, la->evB, 0) != cudaSuccess) return GPINV_ERR_CUDA;
   dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n, 8));
   zero_upper_kernel<<<grd, blk, 0, st>>>(A, n, lda);
   GPINV_CHECK_LAUNCH();

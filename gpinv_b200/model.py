@@ -68,7 +68,7 @@ class Model(Parameterized):
     def _check_infos(self):
         infos, self._pending_infos = self._pending_infos, []
         for info in infos:
-            i = int(info.item())
+            i = int(info.reshape(-1)[0].item())
             if i != 0:
                 raise RuntimeError("Cholesky decomposition was not successful: the matrix is not "
                                    "positive definite at pivot %d" % i)
@@ -86,15 +86,17 @@ class Model(Parameterized):
                    torch.empty(n + 1, dtype=torch.float64).pin_memory())
             self._pinned = {n: pin}
         hin, hout = pin
-        hin.numpy()[...] = x
+        # torch's CPU copy is multi-threaded; a plain numpy assignment of 134 MB is not
+        hin.copy_(torch.from_numpy(x))
         xd = hin.to(dev, non_blocking=True)
         f, g = self._objective_device(xd, **kw)
         hout[:1].copy_(f, non_blocking=True)
         hout[1:].copy_(g, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self._check_infos()
-        out = hout.numpy()
-        return float(out[0]), out[1:].copy()
+        grad = np.empty(n, dtype=np.float64)
+        torch.from_numpy(grad).copy_(hout[1:])
+        return float(hout[0].item()), grad
 
     def compute_log_likelihood(self, **kw):
         x = torch.as_tensor(self.get_free_state()).to(default_device())

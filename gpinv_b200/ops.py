@@ -109,12 +109,12 @@ kcore.register_autograd(_kcore_backward, setup_context=_kcore_setup)
 # --------------------------------------------------------------------------------------
 @torch.library.custom_op("gpinv::potrf", mutates_args=(), device_types="cuda")
 def potrf(K: Tensor) -> Tuple[Tensor, Tensor]:
-    """(L, info): lower Cholesky factor with zeroed strict upper triangle; info int32[1] is the
+    """(L, info): lower Cholesky factor with zeroed strict upper triangle; info[0] (int32) is the
     1-based first failing pivot (0 = success).  GPinv/kernels.py:59."""
     K = _chk(K, "K")
     n = K.shape[0]
     Lm = K.clone()
-    info = torch.zeros(1, dtype=torch.int32, device=K.device)
+    info = torch.zeros(2, dtype=torch.int32, device=K.device)   # [status, scratch ticket]
     rc = _capi.lib().gpinv_potrf_f64(_p(Lm), n, n, _p(info), _st())
     _capi.check(rc, "potrf")
     return Lm, info

@@ -44,7 +44,8 @@ int gpinv_kbuild_bwd_f64(const double* X, const double* X2, int n, int n2, int D
                          int ldkb, double* ls_bar, void* ws, void* stream);
 
 /* --- T4: Cholesky, in place, lower, strict upper zeroed.  Replaces tf.cholesky at
- * GPinv/kernels.py:59, GPinv/kronecker.py:54,57. */
+ * GPinv/kernels.py:59, GPinv/kronecker.py:54,57.  `info` is a device int[2]: info[0] receives the
+ * LAPACK-style status, info[1] is scratch (a ticket counter used by the panel kernel). */
 int gpinv_potrf_f64(double* A, int n, int lda, int* info, void* stream);
 /* reverse (replaces TF's CholeskyGrad): Abar holds Lbar (lower) on entry, the full symmetric
  * dObj/dA on exit. */

@@ -12,4 +12,4 @@ if what != "fwd":
     Lbar = torch.tril(torch.randn(nn, nn, dtype=torch.float64, device=dev))
     G = ops.potrf_bwd(L, Lbar)
 torch.cuda.synchronize()
-print("ok", int(info.item()))
+print("ok", int(info[0].item()))

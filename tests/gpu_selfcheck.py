@@ -82,16 +82,27 @@ def check_potrf():
         Kjunk = K.copy()
         Kd = t(Kjunk).requires_grad_(True)
         L, info = ops.potrf(Kd)
-        report("potrf n=%d (info=%d)" % (n, int(info.item())), rel(L, Lref), 1e-12)
+        report("potrf n=%d (info=%d)" % (n, int(info[0].item())), rel(L, Lref), 1e-12)
         rng = np.random.RandomState(1)
         Lbar = np.tril(rng.randn(n, n))
         (gref,) = torch.autograd.grad((Lref * torch.tensor(Lbar)).sum(), Kt)
         (gout,) = torch.autograd.grad((L * t(Lbar)).sum(), Kd)
         report("potrf_bwd n=%d" % n, rel(gout, gref), 1e-9)
+    # ill-conditioned kernel matrices at the headline size (cond ~1e9); repeated to catch races
+    for n in (3000, 4096):
+        x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)[:, None]
+        K = ops.kcore(x, None, t([0.3]), 1, 1e-6)
+        Lref = torch.linalg.cholesky(K)
+        for rep in range(3):
+            L, info = ops.potrf(K)
+            report("potrf csym n=%d rep %d (info=%d)" % (n, rep, int(info[0].item())),
+                   rel(L, Lref) if int(info[0].item()) == 0 else 1.0, 1e-7)   # vs cuSOLVER at cond(K)~1e9
+        resid = float((L @ L.T - K).abs().max())
+        report("potrf csym n=%d residual |LL^T-K|" % n, resid, 1e-12)
     Kbad = spd(100, 3)
     Kbad[70, 70] = -1.0
     L, info = ops.potrf(t(Kbad))
-    report("potrf info on non-PD (info=%d)" % int(info.item()), 0.0 if int(info.item()) == 71 else 1.0, 0.5)
+    report("potrf info on non-PD (info=%d)" % int(info[0].item()), 0.0 if int(info[0].item()) == 71 else 1.0, 0.5)
 
 
 def check_trsm():
