@@ -26,6 +26,7 @@ _Z = C.c_size_t
 SIGNATURES = {
     "gpinv_version": (_I, []),
     "gpinv_last_error": (C.c_char_p, []),
+    "gpinv_set_workspace": (_I, [_P, _Z]),
     "gpinv_kbuild_ws_bytes": (_Z, [_I, _I, _I]),
     "gpinv_kbuild_f64": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _D, _P, _I, _P, _P]),
     "gpinv_kbuild_bwd_f64": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P]),

@@ -45,7 +45,12 @@ using namespace gpinv;
 
 extern "C" {
 
-int gpinv_version(void) { return 100; }
+int gpinv_version(void) { return 101; }
+
+int gpinv_set_workspace(void* ptr, size_t bytes) {
+  gemm_set_workspace(ptr, bytes);
+  return GPINV_OK;
+}
 const char* gpinv_last_error(void) { return g_last_error.c_str(); }
 
 size_t gpinv_kbuild_ws_bytes(int n, int n2, int D) { return kbuild_ws_bytes(n, n2, D); }

@@ -2,6 +2,7 @@
 #include "gemm.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace gpinv {
 
@@ -23,6 +24,16 @@ int launch_inst(const GemmParams& p, dim3 grid, cudaStream_t stream) {
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
+}
+
+// split-K workspace registry: [int counters[CNT_SLOTS]] [double partial tiles ...]
+constexpr int CNT_SLOTS = 16384;
+struct WsReg { void* ptr = nullptr; size_t bytes = 0; };
+WsReg g_ws[64];
+inline WsReg* ws_for_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  return g_ws[dev].ptr ? &g_ws[dev] : nullptr;
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -48,6 +59,13 @@ template <class Cfg>
 int dispatch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream);
 
 }  // namespace
+
+void gemm_set_workspace(void* ptr, size_t bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  g_ws[dev].ptr = ptr;
+  g_ws[dev].bytes = bytes;
+}
 
 int gemm_tile_count(int M, int N, int K, bool lower, int batch) {
   GemmParams p = {};
@@ -111,7 +129,38 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
     p.vecB = p.vecB && (p.strideB % 2 == 0);
     p.vecO = p.vecO && (p.strideO % 2 == 0);
   }
-  if (use_small(p, (ef & EF_LOWER) != 0)) return dispatch<CfgSmall>(la, lb, ef, p, stream);
+  const bool lower = (ef & EF_LOWER) != 0;
+  const bool small = use_small(p, lower);
+  // ---- wave-quantisation fix: pick a k-split that fills the last wave (big tiles only) ----
+  static const bool no_split = (getenv("GPINV_NO_SPLIT") != nullptr);
+  if (p.allow_split && !no_split && p.splitk == 1 && !(ef & EF_ATOMIC) && !small) {
+    WsReg* w = ws_for_device();
+    int sms = 148;
+    if (w) {
+      const long long T = (long long)tiles_of(p.M, p.N, 128, lower) * p.batch;
+      const int kt_min = (p.kmode == 0) ? cdiv(p.K, 16) : 0;   // uniform-K problems only
+      const size_t tile_bytes = 128 * 128 * sizeof(double);
+      const size_t cap = (w->bytes > CNT_SLOTS * sizeof(int)) ? (w->bytes - CNT_SLOTS * sizeof(int)) / tile_bytes : 0;
+      // time model (us): waves * (k-tiles per slice * 2.1 + fixed per-CTA cost [+ slice exchange])
+      auto model = [&](int s_) {
+        const double waves = (double)((T * s_ + sms - 1) / sms);
+        return waves * ((double)kt_min / s_ * 2.1 + 3.0 + (s_ > 1 ? 6.0 : 0.0));
+      };
+      double best = model(1);
+      int best_s = 1;
+      for (int s = 2; s <= 8; ++s) {
+        if (kt_min / s < 16 || (size_t)(T * s) > cap || T > CNT_SLOTS) break;
+        const double cost = model(s);
+        if (cost < 0.97 * best) { best = cost; best_s = s; }
+      }
+      if (best_s > 1) {
+        p.splitk = best_s;
+        p.ws_cnt = static_cast<int*>(w->ptr);
+        p.ws = reinterpret_cast<double*>(static_cast<char*>(w->ptr) + CNT_SLOTS * sizeof(int));
+      }
+    }
+  }
+  if (small) return dispatch<CfgSmall>(la, lb, ef, p, stream);
   return dispatch<CfgBig>(la, lb, ef, p, stream);
 }
 

@@ -59,6 +59,13 @@ struct GemmParams {
   int splitk;  // >= 1
   int tiles_m, tiles_n;
   int force_cfg;  // 0 auto | 1 big (128x128) | 2 small (64x64)
+  // Workspace split-K (wave-quantisation fix): when splitk > 1 and the epilogue is not the
+  // atomic one, every k-slice CTA stores its partial tile to `ws`, takes a ticket on the tile's
+  // counter, and the LAST arriver sums the slices in fixed order (deterministic) and runs the
+  // fused epilogue.  No CTA ever waits on another.  Enabled per call with allow_split.
+  int allow_split;
+  double* ws;
+  int* ws_cnt;
   int vecA, vecB, vecO;  // 16-byte alignment of operands / output rows
   // batching over blockIdx.z (element strides; 0 = shared operand)
   int batch;
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(cons
     const int last = min(ktiles, first + per);
     kb += first * BK;
     ktiles = max(last - first, 0);
-    if (ktiles == 0) return;
+    if (ktiles == 0 && (EF & EF_ATOMIC)) return;
   }
 
   double acc[TM][TN][2];
@@ -262,6 +269,49 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(cons
     }
   }
   cp_async_wait<0>();
+
+  // ---- workspace split-K: combine the k-slices of this tile ----
+  if (!(EF & EF_ATOMIC) && p.splitk > 1) {
+    const size_t tile_id = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
+    constexpr int TILE = BM * BN;
+    double* mine = p.ws + (tile_id * p.splitk + blockIdx.y) * TILE;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          __stcg(mine + ((i * TN + j) * 2 + e) * THREADS + tid, acc[i][j][e]);
+    __threadfence();
+    __syncthreads();   // all warps are past the main loop: the operand stages are dead
+    int* s_ticket = reinterpret_cast<int*>(smem);
+    if (tid == 0) *s_ticket = atomicAdd(p.ws_cnt + tile_id, 1);
+    __syncthreads();
+    if (*s_ticket != p.splitk - 1) return;
+    if (tid == 0) p.ws_cnt[tile_id] = 0;   // ready for the next launch (stream ordered)
+    __threadfence();
+    const double* base = p.ws + tile_id * p.splitk * TILE + tid;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    // slices in fixed order (bitwise reproducible); all loads of one slice are independent
+    for (int sl = 0; sl < p.splitk; ++sl) {
+      const double* src = base + (size_t)sl * TILE;
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        double tmp[TN][2];
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) tmp[j][e] = __ldcg(src + ((i * TN + j) * 2 + e) * THREADS);
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) acc[i][j][e] += tmp[j][e];
+      }
+    }
+  }
 
   // ---- epilogue ----
   double alpha = p.alpha;
@@ -370,6 +420,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(cons
       }
   }
 }
+
+// Register / query the split-K workspace (device memory owned by the caller; one per device).
+void gemm_set_workspace(void* ptr, size_t bytes);
 
 // Number of CTA tiles the launcher will use for an M x N problem (for split-K heuristics).
 int gemm_tile_count(int M, int N, int K, bool lower, int batch);

@@ -298,7 +298,7 @@ int sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
       p.M = n; p.N = n; p.K = S;
       p.alpha = 1.0;
       p.out = Qbar + (size_t)r * n * n; p.ldo = n;
-      p.kmode = 0; p.splitk = 1;
+      p.kmode = 0; p.splitk = 1; p.allow_split = 1;
       rc = gemm_launch(LMN, LMN, EF_LOWER, p, st);
       if (rc) return rc;
     }
@@ -313,7 +313,7 @@ int sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
       p.out = Lc_bar; p.ldo = ldlb;
       p.W = Lc; p.ldw = ldl;
       p.dot = svdot + r;
-      p.kmode = 0; p.splitk = 1;
+      p.kmode = 0; p.splitk = 1; p.allow_split = 1;
       rc = gemm_launch(LMN, LMN, EF_LOWER | EF_BETA | EF_DOT, p, st);
       if (rc) return rc;
     }
@@ -357,7 +357,7 @@ int abel_fwd_f64(const double* expF, const double* A, int lda, const double* Y, 
   p.colvec = Y;
   p.out = Rs; p.ldo = M;
   p.sumsq = sumsq;
-  p.kmode = 0; p.splitk = 1;
+  p.kmode = 0; p.splitk = 1; p.allow_split = 1;
   return gemm_launch(LK, LK, EF_COLVEC | EF_SUMSQ, p, st);
 }
 
@@ -371,7 +371,7 @@ int abel_bwd_f64(const double* Rs, const double* A, int lda, const double* expF,
   p.alpha = 1.0; p.alpha_dev = coef;
   p.mul = expF; p.ldmul = n;
   p.out = Fbar; p.ldo = n;
-  p.kmode = 0; p.splitk = 1;
+  p.kmode = 0; p.splitk = 1; p.allow_split = 1;
   return gemm_launch(LK, LMN, EF_MULMAT, p, st);
 }
 

@@ -36,6 +36,23 @@ def _chk(t: Tensor, name: str) -> Tensor:
     return t.contiguous()
 
 
+_SPLIT_WS = {}
+
+
+def ensure_workspace(device, nbytes: int = 320 << 20):
+    """Register the (zero-initialised, persistent) split-K workspace for `device` once."""
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _SPLIT_WS:
+        with torch.cuda.device(idx):
+            buf = torch.zeros(nbytes // 8, dtype=torch.float64, device="cuda")
+            torch.cuda.current_stream().synchronize()
+            _capi.check(_capi.lib().gpinv_set_workspace(_p(buf), buf.numel() * 8), "set_workspace")
+        _SPLIT_WS[idx] = buf
+    return _SPLIT_WS[idx]
+
+
 def _ws(nbytes: int, like: Tensor) -> Tensor:
     return torch.empty(max(int(nbytes) // 8 + 2, 2), dtype=torch.float64, device=like.device)
 
@@ -223,6 +240,7 @@ def stvgp_sample_bwd(Lc: Tensor, sqrt_v: Tensor, Q: Tensor, E: Tensor, U: Tensor
     """[Lc_bar, sqrt_v_bar, Qbar, qmu_bar, mean_bar]."""
     Lc = _chk(Lc, "Lc"); sqrt_v = _chk(sqrt_v, "sqrt_v"); Q = _chk(Q, "Q")
     E = _chk(E, "E"); U = _chk(U, "U"); Fbar = _chk(Fbar, "Fbar")
+    ensure_workspace(E.device)
     if klbar is not None:
         klbar = _chk(klbar, "klbar")
     R, S, n = E.shape
@@ -312,6 +330,7 @@ def abel_resid(F: Tensor, expF: Tensor, A: Tensor, Y: Tensor) -> Tuple[Tensor, T
     """(sumsq [1], Rs [S,M]) with Rs = 1 y^T - exp(F) A^T.  F, expF [S,n]; A [M,n]; Y [M].
     `expF` must equal exp(F) (it is the second output of stvgp_sample); gradients flow to F."""
     expF = _chk(expF, "expF"); A = _chk(A, "A"); Y = _chk(Y, "Y")
+    ensure_workspace(expF.device)
     S, n = expF.shape
     M = A.shape[0]
     Rs = torch.empty((S, M), dtype=torch.float64, device=expF.device)

@@ -31,6 +31,11 @@ extern "C" {
 int gpinv_version(void);
 const char* gpinv_last_error(void);
 
+/* Optional scratch for the GEMM kernel's split-K wave-quantisation fix: device memory owned by
+ * the caller, ZERO-INITIALISED, registered once per device (first 64 KB are tile counters).
+ * Without it the GEMMs run data-parallel only.  Calls that use it must be stream-ordered. */
+int gpinv_set_workspace(void* ptr, size_t bytes);
+
 /* --- T1-T3: kernel core matrix.  Replaces Kern._Kcore + jitter (GPinv/kernels.py:57-58,
  * 105-107,115-120,140-145; GPflow Stationary.square_dist).  X [n,D], X2 [n2,D] or NULL
  * (then K is n x n and `jitter` is added to its diagonal); ls device [D] (ard) or [1]. */
