@@ -247,16 +247,18 @@ def main():
     if rank == 0:
         from gpinv_b200 import ops
         Sl = S // world
-        Xm = torch.randn(Sl, n, dtype=torch.float64, device=dev)
+        Fm = 0.1 * torch.randn(Sl, n, dtype=torch.float64, device=dev)
+        Xm = torch.exp(Fm)
         Am = m.likelihood.Amat.tensor()
+        Ym = m.Y.tensor().reshape(-1).contiguous()
         for _ in range(3):
-            ops.gemm(Xm, Am, False, True, False)
+            ops.abel_resid(Fm, Xm, Am, Ym)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 10
         a.record()
         for _ in range(reps):
-            ops.gemm(Xm, Am, False, True, False)
+            ops.abel_resid(Fm, Xm, Am, Ym)
         b.record()
         torch.cuda.synchronize()
         tk = a.elapsed_time(b) / reps / 1e3
@@ -274,7 +276,9 @@ def main():
         peak = 2 * 4096 ** 3 / best / 1e12
         ach = 2.0 * Sl * n * M / tk / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_dmma_kernel<LK,LK,COLVEC|SUMSQ> (Abel transform R = y - exp(F) A^T)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": (614.0e6 if (world == 1 and args.config == "cfg5") else None),
+                "traffic_note": "dram__bytes_read+write per launch from profiles/r1_abel_gemm_ncu_full.txt (369 MB algorithmic operands+result, rest = split-K slice exchange)",
                 "peak_source": "cuBLAS DGEMM 4096^3 best-of-6 measured in this run (fp64 DMMA; MEASURED_PEAKS.json has no fp64 figure)",
                 "whole_eval_achieved": work_flops(n, M, S, world) / t_dev * K / 1e12,
                 "whole_eval_frac": work_flops(n, M, S, world) / t_dev * K / 1e12 / peak}
