@@ -34,10 +34,10 @@ def work_flops(n, M, S, G=1, k=1, R=1):
 
 
 def make_inputs(n, M, S):
-    from oracle import gpinv_oracle as O      # input generator only (vectorised make_LosMatrix)
+    from gpinv_b200.los import make_LosMatrix
     r = np.linspace(0, 1., n)
     z = np.linspace(-0.9, 0.9, M)
-    A = O.make_los_matrix(r, z)
+    A = make_LosMatrix(r, z)
     g = np.exp(-(r - 0.3) ** 2 / 0.1) + np.exp(-(r + 0.3) ** 2 / 0.1)
     y = A @ g + 0.1 * np.random.RandomState(0).randn(M)
     rng = np.random.RandomState(1)

@@ -44,6 +44,8 @@ SIGNATURES = {
     "gpinv_gauss_bwd_f64": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "gpinv_abel_fwd_f64": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
     "gpinv_abel_bwd_f64": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),
+    "gpinv_spec_fwd_f64": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "gpinv_spec_bwd_f64": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gpinv_sumsq_f64": (_I, [_P, _Z, _P, _P]),
 }
 

@@ -38,6 +38,10 @@ int abel_fwd_f64(const double*, const double*, int, const double*, int, int, int
                  cudaStream_t);
 int abel_bwd_f64(const double*, const double*, int, const double*, const double*, int, int, int,
                  double*, cudaStream_t);
+int spec_fwd_f64(const double*, const double*, const double*, const double*, const double*, int, int,
+                 int, int, double*, double*, cudaStream_t);
+int spec_bwd_f64(const double*, const double*, const double*, const double*, const double*,
+                 const double*, const double*, int, int, int, int, double*, cudaStream_t);
 }  // namespace gpinv
 
 using namespace gpinv;
@@ -151,6 +155,17 @@ int gpinv_abel_fwd_f64(const double* expF, const double* A, int lda, const doubl
 int gpinv_abel_bwd_f64(const double* Rs, const double* A, int lda, const double* expF,
                        const double* coef, int n, int M, int S, double* Fbar, void* stream) {
   return abel_bwd_f64(Rs, A, lda, expF, coef, n, M, S, Fbar, ST(stream));
+}
+
+int gpinv_spec_fwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
+                       const double* Y, int n, int m, int k, int S, double* P, double* sumsq,
+                       void* stream) {
+  return spec_fwd_f64(F, A, cosT, lam, Y, n, m, k, S, P, sumsq, ST(stream));
+}
+int gpinv_spec_bwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
+                       const double* Y, const double* P, const double* coef, int n, int m, int k,
+                       int S, double* Fbar, void* stream) {
+  return spec_bwd_f64(F, A, cosT, lam, Y, P, coef, n, m, k, S, Fbar, ST(stream));
 }
 
 int gpinv_sumsq_f64(const double* x, size_t count, double* out, void* stream) {

@@ -1,0 +1,125 @@
+// Spectroscopic Abel transform (T16) and its reverse:
+//   P[s,k,m] = sum_j A[m,j] a_j/(sqrt(2 pi) s_j) exp(-((lam_k - v_j cosT[m,j])/s_j)^2 / 2),
+//   a = exp(F0[s,j]), s = exp(F1[s,j]), v = F2[s,j]
+// (notebooks/Spectroscopic_Abel_inversion.ipynb:316-346; the reference tiles six [S,k,m,n]
+// tensors).  Not a GEMM: the exponent depends on (k,m,j) jointly, so this is an FP64-pipe bound
+// fused evaluate-and-reduce with the per-sample latent profile staged in shared memory.
+#include "common.cuh"
+
+namespace gpinv {
+
+#define SPEC_MAX_N 2048
+constexpr double INV_SQRT_2PI = 0.3989422804014326779399460599343819;
+
+// grid (ceil(k*m/256), S); thread = one (wavelength, chord) pair, wavelength fastest so a warp
+// shares the chord row of A / cosT (broadcast loads).
+__global__ void __launch_bounds__(256) spec_fwd_kernel(const double* __restrict__ F,
+                                                       const double* __restrict__ A,
+                                                       const double* __restrict__ cosT,
+                                                       const double* __restrict__ lam,
+                                                       const double* __restrict__ Y, int n, int m,
+                                                       int k, int S, double* __restrict__ P,
+                                                       double* __restrict__ sumsq) {
+  extern __shared__ __align__(16) double sm[];
+  double* amp = sm;          // a_j / (sqrt(2 pi) s_j)
+  double* invs = amp + n;    // 1 / s_j
+  double* vel = invs + n;    // v_j
+  __shared__ double red[32];
+  const int s = blockIdx.y;
+  const size_t Sn = (size_t)S * n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double f0 = F[(size_t)s * n + j], f1 = F[Sn + (size_t)s * n + j];
+    const double is = exp(-f1);
+    amp[j] = exp(f0) * is * INV_SQRT_2PI;
+    invs[j] = is;
+    vel[j] = F[2 * Sn + (size_t)s * n + j];
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0;
+  if (p < k * m) {
+    const int mm = p / k, kk = p % k;
+    const double l = lam[kk];
+    const double* a_row = A + (size_t)mm * n;
+    const double* c_row = cosT + (size_t)mm * n;
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) {
+      const double z = (l - vel[j] * c_row[j]) * invs[j];
+      acc += a_row[j] * amp[j] * exp(-0.5 * z * z);
+    }
+    if (P) P[((size_t)s * k + kk) * m + mm] = acc;
+    if (Y) {
+      const double d = acc - Y[(size_t)kk * m + mm];
+      d2 = d * d;
+    }
+  }
+  if (sumsq) {
+    d2 = block_sum(d2, red);
+    if (threadIdx.x == 0) atomicAdd(sumsq, d2);
+  }
+}
+
+// grid (n, S); one block reduces over all (k,m) pairs for one (sample, radial point):
+//   Fbar_c[s,j] = coef * sum_{k,m} (P - Y) dt/dF_c
+__global__ void __launch_bounds__(256) spec_bwd_kernel(const double* __restrict__ F,
+                                                       const double* __restrict__ A,
+                                                       const double* __restrict__ cosT,
+                                                       const double* __restrict__ lam,
+                                                       const double* __restrict__ Y,
+                                                       const double* __restrict__ P,
+                                                       const double* __restrict__ coef, int n,
+                                                       int m, int k, int S,
+                                                       double* __restrict__ Fbar) {
+  __shared__ double red[32];
+  const int j = blockIdx.x, s = blockIdx.y;
+  const size_t Sn = (size_t)S * n;
+  const double f0 = F[(size_t)s * n + j], f1 = F[Sn + (size_t)s * n + j];
+  const double is = exp(-f1);
+  const double amp = exp(f0) * is * INV_SQRT_2PI;
+  const double v = F[2 * Sn + (size_t)s * n + j];
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+  const int total = k * m;
+  for (int p = threadIdx.x; p < total; p += blockDim.x) {
+    const int kk = p / m, mm = p % m;   // chord fastest: P and Y reads are coalesced
+    const double a = A[(size_t)mm * n + j];
+    if (a == 0.0) continue;
+    const double ct = cosT[(size_t)mm * n + j];
+    const double z = (lam[kk] - v * ct) * is;
+    const double t = a * amp * exp(-0.5 * z * z);
+    const double r = P[((size_t)s * k + kk) * m + mm] - Y[(size_t)kk * m + mm];
+    const double rt = r * t;
+    g0 += rt;
+    g1 += rt * (z * z - 1.0);
+    g2 += rt * z * ct * is;
+  }
+  const double c = coef[0];
+  g0 = block_sum(g0, red);
+  if (threadIdx.x == 0) Fbar[(size_t)s * n + j] = c * g0;
+  g1 = block_sum(g1, red);
+  if (threadIdx.x == 0) Fbar[Sn + (size_t)s * n + j] = c * g1;
+  g2 = block_sum(g2, red);
+  if (threadIdx.x == 0) Fbar[2 * Sn + (size_t)s * n + j] = c * g2;
+}
+
+int spec_fwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
+                 const double* Y, int n, int m, int k, int S, double* P, double* sumsq,
+                 cudaStream_t st) {
+  if (n <= 0 || n > SPEC_MAX_N || m <= 0 || k <= 0 || S <= 0) return GPINV_ERR_ARG;
+  if (sumsq && cudaMemsetAsync(sumsq, 0, sizeof(double), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  dim3 grid(cdiv(k * m, 256), S);
+  spec_fwd_kernel<<<grid, 256, 3 * n * sizeof(double), st>>>(F, A, cosT, lam, Y, n, m, k, S, P, sumsq);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
+int spec_bwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
+                 const double* Y, const double* P, const double* coef, int n, int m, int k, int S,
+                 double* Fbar, cudaStream_t st) {
+  if (n <= 0 || m <= 0 || k <= 0 || S <= 0) return GPINV_ERR_ARG;
+  dim3 grid(n, S);
+  spec_bwd_kernel<<<grid, 256, 0, st>>>(F, A, cosT, lam, Y, P, coef, n, m, k, S, Fbar);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
+}  // namespace gpinv

@@ -114,8 +114,11 @@ class SpecAbelLikelihood(Likelihood):
         self.variance = Param(np.ones(1), transforms.positive)
 
     def sample_F(self, F):
-        if hasattr(ops, "spec_transform"):
-            return ops.spec_transform(_internal(F), self.Amat, self.cosT, self.lam.reshape(-1).contiguous())
+        """[S,k,m] transformed samples (fused sm_100a kernel)."""
+        return ops.spec_transform(_internal(F), self.Amat, self.cosT, self.lam.reshape(-1).contiguous())
+
+    def sample_F_torch(self, F):
+        """The notebook's tile-and-reduce formulation in torch ops (kept for user subclasses)."""
         a = torch.exp(F[:, :, 0])[:, None, None, :]
         s = torch.exp(F[:, :, 1])[:, None, None, :]
         v = F[:, :, 2][:, None, None, :]
@@ -124,13 +127,13 @@ class SpecAbelLikelihood(Likelihood):
         return torch.sum(self.Amat[None, None] * f, 3)
 
     def logp(self, F, Y):
-        f_samples = self.sample_F(F)
+        f_samples = self.sample_F_torch(F)
         return densities.gaussian(f_samples, Y[None].expand(f_samples.shape[0], -1, -1), self.variance)
 
     def logp_sum(self, F, Y, expF=None):
-        P = self.sample_F(F)
+        ss, P = ops.spec_resid(_internal(F), self.Amat, self.cosT, self.lam.reshape(-1).contiguous(),
+                               Y.contiguous())
         var = self.variance
-        ss = torch.sum(torch.square(P - Y[None]))
         return -0.5 * float(P.numel()) * (LOG2PI + torch.log(var)) - 0.5 * ss / var
 
     def sample_Y(self, F):

@@ -373,3 +373,56 @@ def sumsq(x: Tensor) -> Tensor:
     out = torch.empty(1, dtype=torch.float64, device=x.device)
     _capi.check(_capi.lib().gpinv_sumsq_f64(_p(x), x.numel(), _p(out), _st()), "sumsq")
     return out
+
+
+# --------------------------------------------------------------------------------------
+# T16 spectroscopic Abel transform
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("gpinv::spec_transform", mutates_args=(), device_types="cuda")
+def spec_transform(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor) -> Tensor:
+    """P [S,k,m] from F [3,S,n] (notebooks/Spectroscopic_Abel_inversion.ipynb:316-346)."""
+    F = _chk(F, "F"); A = _chk(A, "A"); cosT = _chk(cosT, "cosT"); lam = _chk(lam, "lam")
+    _, S, n = F.shape
+    m, k = A.shape[0], lam.numel()
+    P = torch.empty((S, k, m), dtype=torch.float64, device=F.device)
+    rc = _capi.lib().gpinv_spec_fwd_f64(_p(F), _p(A), _p(cosT), _p(lam), None, n, m, k, S, _p(P), None, _st())
+    _capi.check(rc, "spec_fwd")
+    return P
+
+
+@torch.library.custom_op("gpinv::spec_resid", mutates_args=(), device_types="cuda")
+def spec_resid(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, Y: Tensor) -> Tuple[Tensor, Tensor]:
+    """(sum (P - Y)^2 [1], P [S,k,m])."""
+    F = _chk(F, "F"); A = _chk(A, "A"); cosT = _chk(cosT, "cosT"); lam = _chk(lam, "lam"); Y = _chk(Y, "Y")
+    _, S, n = F.shape
+    m, k = A.shape[0], lam.numel()
+    P = torch.empty((S, k, m), dtype=torch.float64, device=F.device)
+    ss = torch.empty(1, dtype=torch.float64, device=F.device)
+    rc = _capi.lib().gpinv_spec_fwd_f64(_p(F), _p(A), _p(cosT), _p(lam), _p(Y), n, m, k, S, _p(P), _p(ss), _st())
+    _capi.check(rc, "spec_fwd")
+    return ss, P
+
+
+@torch.library.custom_op("gpinv::spec_bwd", mutates_args=(), device_types="cuda")
+def spec_bwd(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, Y: Tensor, P: Tensor, coef: Tensor) -> Tensor:
+    F = _chk(F, "F"); P = _chk(P, "P"); coef = _chk(coef, "coef")
+    _, S, n = F.shape
+    m, k = A.shape[0], lam.numel()
+    out = torch.empty_like(F)
+    rc = _capi.lib().gpinv_spec_bwd_f64(_p(F), _p(A), _p(cosT), _p(lam), _p(Y), _p(P), _p(coef), n, m, k, S,
+                                        _p(out), _st())
+    _capi.check(rc, "spec_bwd")
+    return out
+
+
+def _spec_setup(ctx, inputs, output):
+    F, A, cosT, lam, Y = inputs
+    ctx.save_for_backward(F, A, cosT, lam, Y, output[1])
+
+
+def _spec_backward(ctx, g_ss, g_p_unused):
+    F, A, cosT, lam, Y, P = ctx.saved_tensors
+    return spec_bwd(F, A, cosT, lam, Y, P, (2.0 * g_ss).reshape(1).contiguous()), None, None, None, None
+
+
+spec_resid.register_autograd(_spec_backward, setup_context=_spec_setup)

@@ -105,6 +105,17 @@ int gpinv_abel_fwd_f64(const double* expF, const double* A, int lda, const doubl
 int gpinv_abel_bwd_f64(const double* Rs, const double* A, int lda, const double* expF,
                        const double* coef, int n, int M, int S, double* Fbar, void* stream);
 
+/* --- T16: spectroscopic Abel transform (notebooks/Spectroscopic_Abel_inversion.ipynb:316-356).
+ * F [3,S,n] = (log a, log sigma, v); A, cosT [m,n]; lam [k]; Y [k,m] (may be NULL with sumsq).
+ * fwd: P [S,k,m] (may be NULL), *sumsq = sum (P - Y)^2 (may be NULL);
+ * bwd: Fbar [3,S,n] = coef * sum_{k,m} (P - Y) dP/dF, coef a device scalar. */
+int gpinv_spec_fwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
+                       const double* Y, int n, int m, int k, int S, double* P, double* sumsq,
+                       void* stream);
+int gpinv_spec_bwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
+                       const double* Y, const double* P, const double* coef, int n, int m, int k,
+                       int S, double* Fbar, void* stream);
+
 /* --- reductions used by T8/T11/T17 */
 int gpinv_sumsq_f64(const double* x, size_t count, double* out, void* stream);
 

@@ -182,6 +182,21 @@ def check_liks():
         (gout,) = torch.autograd.grad(ss.sum(), Fd)
         report("abel_resid n=%d M=%d S=%d" % (n, M, S), rel(ss, ref.reshape(1)), 1e-13)
         report("abel_resid bwd", rel(gout, gref), 1e-12)
+    for (n, m, k, S) in [(12, 9, 7, 3), (30, 40, 50, 5), (64, 33, 70, 9)]:
+        from tests.helpers import spec_data
+        r, A, cosT, lam, y = spec_data(n, m, k)
+        F = np.stack([-1.0 + 0.3 * rng.randn(S, n), -0.5 + 0.2 * rng.randn(S, n), 0.5 * rng.randn(S, n)], 0)
+        Ft = torch.tensor(F, requires_grad=True)
+        Pref = O.spec_abel_transform(Ft.permute(1, 2, 0), torch.tensor(A), torch.tensor(cosT), torch.tensor(lam))
+        ref = ((Pref - torch.tensor(y)[None]) ** 2).sum()
+        (gref,) = torch.autograd.grad(ref, Ft)
+        Fd = t(F).requires_grad_(True)
+        ss, P = ops.spec_resid(Fd, t(A), t(cosT), t(lam), t(y))
+        (gout,) = torch.autograd.grad(ss.sum(), Fd)
+        report("spec_resid P n=%d m=%d k=%d S=%d" % (n, m, k, S), rel(P, Pref), 1e-13)
+        report("spec_resid sumsq", rel(ss, ref.reshape(1)), 1e-13)
+        report("spec_resid bwd", rel(gout, gref), 1e-12)
+        report("spec_transform", rel(ops.spec_transform(t(F), t(A), t(cosT), t(lam)), Pref), 1e-13)
     x = rng.randn(100001)
     report("sumsq", rel(ops.sumsq(t(x)), torch.tensor([np.sum(x * x)])), 1e-13)
 

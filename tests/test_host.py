@@ -186,6 +186,15 @@ def test_sample_sharding_world_size_2_gloo(tmp_path):
     assert codes == [0, 0], codes
 
 
+def test_los_generators_match_the_loop_restatement():
+    from gpinv_b200 import los
+    r, z = np.linspace(0, 1, 30), np.linspace(-0.9, 0.9, 40)
+    assert np.array_equal(los.make_LosMatrix(r, z), O.make_los_matrix_loops(r, z))
+    assert np.array_equal(los.make_cosTheta(r, z), O.make_cos_theta(r, z))
+    r, z = np.linspace(0, 1, 17), np.linspace(-1.1, 1.1, 23)      # chords outside the plasma
+    assert np.array_equal(los.make_LosMatrix(r, z), O.make_los_matrix_loops(r, z))
+
+
 def test_shard_bounds():
     from gpinv_b200.dist import DistContext
     c = DistContext(rank=3, world_size=8)
