@@ -32,6 +32,8 @@ class Model(Parameterized):
         self._pending_infos = []
         self.dist = None            # set by gpinv_b200.dist.attach()
         self._pinned = {}
+        self._use_graph = False
+        self._graphs = {}
 
     # ---- to be provided by subclasses ----------------------------------------------
     def build_likelihood(self, **kw):
@@ -41,8 +43,54 @@ class Model(Parameterized):
         """Hook called before every evaluation (StVGP re-creates q_mu/q_sqrt when X changed)."""
 
     # ---- objective -------------------------------------------------------------------
+    def enable_cuda_graph(self, flag=True):
+        """Capture one whole evaluation (forward + hand-written backward, ~100-250 kernel launches)
+        in a CUDA graph and replay it: the small configurations are launch-latency bound.  The
+        returned tensors are the graph's static outputs (valid until the next evaluation)."""
+        self._use_graph = bool(flag)
+        self._graphs = {}
+        return self
+
+    def _graph_inputs(self, kw):
+        """Tensors that vary between evaluations besides x (StVGP: the eps draws)."""
+        return {}
+
     def _objective_device(self, x: torch.Tensor, **kw):
         """(-f, -df/dx) as CUDA tensors ([1] and [|x|]); no host synchronisation."""
+        if self._use_graph and self.dist is None:
+            return self._objective_graphed(x, **kw)
+        return self._objective_eager(x, **kw)
+
+    def _objective_graphed(self, x, **kw):
+        self._prepare()
+        dyn = self._graph_inputs(kw)
+        key = (x.numel(),) + tuple((k, tuple(v.shape)) for k, v in sorted(dyn.items()))
+        ent = self._graphs.get(key)
+        if ent is None:
+            sx = x.detach().clone()
+            sdyn = {k: v.detach().clone() for k, v in dyn.items()}
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):      # warm-up: lazy attribute setting, workspace registration
+                    self._objective_eager(sx, **sdyn)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                f, g = self._objective_eager(sx, **sdyn)
+            ent = (graph, sx, sdyn, f, g, list(self._pending_infos))
+            self._graphs[key] = ent
+        graph, sx, sdyn, f, g, infos = ent
+        sx.copy_(x)
+        for k, v in dyn.items():
+            sdyn[k].copy_(v)
+        graph.replay()
+        self._pending_infos = list(infos)
+        return f, g
+
+    def _objective_eager(self, x: torch.Tensor, **kw):
         self._prepare()
         leaves = self.make_tensors(x)
         self._pending_infos = []

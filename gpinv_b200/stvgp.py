@@ -74,6 +74,11 @@ class StVGP(GPModel):
             eps = self.dist.shard_samples(eps)
         return eps.contiguous()
 
+    def _graph_inputs(self, kw):
+        eps = kw.get("eps")
+        S = self.num_samples if eps is None else eps.shape[1]
+        return {"eps": self._eps_tensor(eps, S)}
+
     def build_likelihood(self, eps=None):
         """Variational lower bound with stochastic approximation (GPinv/stvgp.py:96-107)."""
         S_global = self.num_samples if eps is None else eps.shape[1]

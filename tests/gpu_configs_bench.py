@@ -1,0 +1,112 @@
+"""evals/s of every BASELINE.json config on the GPU (device-resident and host-API) next to the
+oracle on the host CPU.  Prints one line per config; used for DESIGN.md section 6."""
+import os, sys, time, json
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gpinv_b200 import gpmc, kernels, kronecker, likelihoods, mean_functions, stvgp
+from gpinv_b200.los import make_LosMatrix, make_cosTheta
+from oracle import gpinv_oracle as O
+from tests.helpers import abel_data, spec_data, spec_from_model
+
+dev = torch.device("cuda:0")
+
+
+def time_gpu(m, x, eps, iters):
+    xd = torch.as_tensor(x).to(dev)
+    ed = None if eps is None else torch.as_tensor(eps).to(dev)
+    kw = {} if eps is None else {"eps": ed}
+    for _ in range(3):
+        m._objective_device(xd, **kw)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        m._objective_device(xd, **kw)
+    b.record()
+    torch.cuda.synchronize()
+    t_dev = a.elapsed_time(b) / iters / 1e3
+    kw = {} if eps is None else {"eps": eps}
+    m._objective(x, **kw)
+    t0 = time.perf_counter()
+    for _ in range(max(3, iters // 4)):
+        m._objective(x, **kw)
+    t_host = (time.perf_counter() - t0) / max(3, iters // 4)
+    return t_dev, t_host
+
+
+def time_cpu(m, x, eps, max_s=20.0):
+    spec = spec_from_model(m)
+    O.objective(spec, x, eps)
+    ts = []
+    t_end = time.time() + max_s
+    while len(ts) < 2 or (time.time() < t_end and len(ts) < 8):
+        t0 = time.time()
+        O.objective(spec, x, eps)
+        ts.append(time.time() - t0)
+    return min(ts)
+
+
+def report(name, m, eps, iters, cpu=True, extra=""):
+    x = m.get_free_state()
+    t_dev, t_host = time_gpu(m, x, eps, iters)
+    t_cpu = time_cpu(m, x, eps) if cpu else float("nan")
+    try:
+        m.enable_cuda_graph()
+        tg_dev, tg_host = time_gpu(m, x, eps, iters)
+        extra += " | CUDA graph: device %.2f evals/s (%.3f ms) host-API %.2f evals/s" % (1 / tg_dev, 1e3 * tg_dev, 1 / tg_host)
+    except Exception as e:
+        extra += " | CUDA graph failed: %r" % (e,)
+    m.enable_cuda_graph(False)
+    print("%-34s |x|=%9d  GPU device %9.2f evals/s (%8.3f ms)  GPU host-API %9.2f evals/s  CPU oracle %8.2f evals/s (%d thr) %s"
+          % (name, x.size, 1 / t_dev, 1e3 * t_dev, 1 / t_host, 1 / t_cpu, torch.get_num_threads(), extra), flush=True)
+
+
+def main():
+    which = sys.argv[1:] or ["1", "2", "3a", "3b", "4"]
+    rng = np.random.RandomState(1)
+    if "1" in which:
+        r, z, A, y = abel_data(30, 40)
+        m = stvgp.StVGP(r[:, None], y[:, None], kernels.RBF_csym(1, 1), likelihoods.AbelLikelihood(A),
+                        mean_functions.Constant(1), num_samples=10)
+        report("cfg1 Abel StVGP n=30 M=40 S=10", m, np.random.RandomState(2).randn(1, 10, 30), 50)
+    if "2" in which:
+        n, S = 1024, 256
+        X = np.linspace(0, 6, n)[:, None]
+        Y = np.sin(X) + 0.3 * np.random.RandomState(0).randn(n, 1)
+        m = stvgp.StVGP(X, Y, kernels.RBF(1, 1), likelihoods.Gaussian(), num_samples=S)
+        m.kern.lengthscales = 0.5
+        m.likelihood.variance = 0.09
+        m.q_mu = 0.3 * rng.randn(n, 1)
+        m.q_sqrt = (0.5 * np.eye(n) + 0.05 / np.sqrt(n) * np.tril(rng.randn(n, n)))[:, :, None]
+        report("cfg2 GP regression n=1024 S=256", m, np.random.RandomState(2).randn(1, S, n), 30)
+    if "3a" in which:
+        n, M, nl, S = 64, 64, 128, 256
+        r, A, cosT, lam, y = spec_data(n, M, nl)
+        ka = kernels.RBF_csym(1, 2); ka.lengthscales = 0.3
+        kv = kernels.RBF_casym(1, 1); kv.lengthscales = 0.3
+        m = stvgp.StVGP(r[:, None], y, kernels.Stack([ka, kv]), likelihoods.SpecAbelLikelihood(A, cosT, lam),
+                        mean_functions.Stack([mean_functions.Constant(2, c=-2 * np.ones(2)), mean_functions.Zero(1)]),
+                        num_latent=3, num_samples=S)
+        report("cfg3a spectroscopic n=64 R=3 S=256", m, np.random.RandomState(2).randn(3, S, n), 20)
+    if "3b" in which:
+        d1, d2 = np.linspace(0, 1, 64), np.linspace(-3, 3, 128)
+        X = np.array([[a, b] for a in d1 for b in d2])
+        n, R, S = X.shape[0], 3, 256
+        Y = rng.randn(n, R)
+        m = stvgp.StVGP(X, Y, kronecker.RBF2D(1, R, d1[:, None], d2[:, None]), likelihoods.Gaussian(),
+                        q_diag=True, num_samples=S)
+        report("cfg3b Kronecker 64x128 R=3 S=256", m, np.random.RandomState(2).randn(R, S, n), 20, cpu=False,
+               extra="(oracle builds the dense 8192^2 factor: not timed)")
+    if "4" in which:
+        n = 2048
+        r, z, A, y = abel_data(n, n)
+        m = gpmc.GPMC(r[:, None], y[:, None], kernels.RBF_csym(1, 1), likelihoods.AbelLikelihood(A),
+                      mean_functions.Constant(1))
+        m.kern.lengthscales = 0.3
+        m.V = 0.5 * rng.randn(n, 1)
+        report("cfg4 GPMC Abel n=2048 (leapfrog)", m, None, 20)
+
+
+if __name__ == "__main__":
+    main()

@@ -256,3 +256,37 @@ def test_cholesky_failure_raises():
             m._objective(m.get_free_state())
     finally:
         settings.numerics.jitter_level = old
+
+
+def test_cuda_graph_replay_matches_eager():
+    gpmc, kernels, kronecker, likelihoods, mean_functions, stvgp = _gp()
+    m = make_abel_stvgp(30, 40, 10)
+    x = perturbed_state(m)
+    eps = np.random.RandomState(2).randn(1, 10, 30)
+    f0, g0 = m._objective(x, eps=eps)
+    m.enable_cuda_graph()
+    for k in range(3):
+        xk = x + 0.01 * k
+        fe, ge = m.enable_cuda_graph(False)._objective(xk, eps=eps)
+        fg, gg = m.enable_cuda_graph(True)._objective(xk, eps=eps) if k == 0 else m._objective(xk, eps=eps)
+        assert abs(fg - fe) <= 1e-11 * abs(fe) and rel_err(gg, ge) <= 1e-11
+    # a larger problem exercises the look-ahead side stream inside the capture
+    m = make_abel_stvgp(700, 300, 16)
+    m.kern.lengthscales = 0.3
+    x = perturbed_state(m, 0.02)
+    eps = np.random.RandomState(3).randn(1, 16, 700)
+    fe, ge = m._objective(x, eps=eps)
+    m.enable_cuda_graph()
+    for _ in range(2):
+        fg, gg = m._objective(x, eps=eps)
+        assert abs(fg - fe) <= 1e-10 * abs(fe) and rel_err(gg, ge) <= 1e-10
+    # GPMC (no eps input)
+    r, z, A, y = abel_data(30, 40)
+    mc = gpmc.GPMC(r[:, None], y[:, None], kernels.RBF_csym(1, 1), likelihoods.AbelLikelihood(A),
+                   mean_functions.Constant(1))
+    xc = perturbed_state(mc, 0.5)
+    fe, ge = mc._objective(xc)
+    mc.enable_cuda_graph()
+    fg, gg = mc._objective(xc)
+    fg, gg = mc._objective(xc)
+    assert abs(fg - fe) <= 1e-11 * abs(fe) and rel_err(gg, ge) <= 1e-11
