@@ -46,7 +46,7 @@ inline int tiles_of(int M, int N, int bm, bool lower) {
 // Small tiles when the big-tile grid cannot fill the machine or K is too short to amortise a
 // 128x128 tile's fill / epilogue.
 inline bool use_small(const GemmParams& p, bool lower) {
-  if (p.force_cfg == 1) return false;
+  if (p.force_cfg == 1 || p.force_cfg == 3) return false;
   if (p.force_cfg == 2) return true;
   const int batch = p.batch > 1 ? p.batch : 1;
   const long long big_tiles = (long long)tiles_of(p.M, p.N, 128, lower) * batch * (p.splitk > 1 ? p.splitk : 1);
@@ -131,27 +131,74 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
   }
   const bool lower = (ef & EF_LOWER) != 0;
   const bool small = use_small(p, lower);
-  // ---- wave-quantisation fix: pick a k-split that fills the last wave (big tiles only) ----
+  // ---- k-split planning (big tiles only): list-schedule the CTAs in launch order on the SMs
+  // with a per-CTA time model and keep the split factor with the smallest makespan.  Fixes wave
+  // quantisation (uniform K) and the long-tile imbalance of the triangular products.
   static const bool no_split = (getenv("GPINV_NO_SPLIT") != nullptr);
   if (p.allow_split && !no_split && p.splitk == 1 && !(ef & EF_ATOMIC) && !small) {
     WsReg* w = ws_for_device();
-    int sms = 148;
-    if (w) {
-      const long long T = (long long)tiles_of(p.M, p.N, 128, lower) * p.batch;
-      const int kt_min = (p.kmode == 0) ? cdiv(p.K, 16) : 0;   // uniform-K problems only
+    const int tm_ = cdiv(p.M, 128), tn_ = cdiv(p.N, 128);
+    const int T1 = lower ? tm_ * (tm_ + 1) / 2 : tm_ * tn_;
+    const long long T = (long long)T1 * p.batch;
+    // the plan only depends on the problem geometry: cache it (the simulation costs ~1 ms of host time)
+    struct PlanKey { int M, N, K, kmode, lower, batch; };
+    static thread_local PlanKey cache_key[64];
+    static thread_local int cache_val[64];
+    static thread_local int cache_n = 0;
+    int cached = -1;
+    for (int i = 0; i < cache_n; ++i) {
+      const PlanKey& c = cache_key[i];
+      if (c.M == p.M && c.N == p.N && c.K == p.K && c.kmode == p.kmode && c.lower == (int)lower && c.batch == p.batch) {
+        cached = cache_val[i];
+        break;
+      }
+    }
+    if (w && cached > 1) {
+      p.splitk = cached;
+      p.ws_cnt = static_cast<int*>(w->ptr);
+      p.ws = reinterpret_cast<double*>(static_cast<char*>(w->ptr) + CNT_SLOTS * sizeof(int));
+    } else if (w && cached < 0 && T <= CNT_SLOTS && T1 <= 4096) {
       const size_t tile_bytes = 128 * 128 * sizeof(double);
       const size_t cap = (w->bytes > CNT_SLOTS * sizeof(int)) ? (w->bytes - CNT_SLOTS * sizeof(int)) / tile_bytes : 0;
-      // time model (us): waves * (k-tiles per slice * 2.1 + fixed per-CTA cost [+ slice exchange])
-      auto model = [&](int s_) {
-        const double waves = (double)((T * s_ + sms - 1) / sms);
-        return waves * ((double)kt_min / s_ * 2.1 + 3.0 + (s_ > 1 ? 6.0 : 0.0));
+      static thread_local int kt[4096];
+      for (int i = 0; i < T1; ++i) {
+        int tm, tn, kb, ke;
+        gemm_decode_tile(i, tm_, tn_, p.kmode, lower, tm, tn);
+        gemm_krange(p.kmode, p.K, tm * 128, tn * 128, 128, 128, 16, kb, ke);
+        kt[i] = (ke > kb) ? cdiv(ke - kb, 16) : 0;
+      }
+      const int sms = 148;
+      auto makespan = [&](int s_) {
+        double busy[148];
+        for (int i = 0; i < sms; ++i) busy[i] = 0.0;
+        // launch order: blockIdx.x fastest, then the slice index, then the batch
+        for (int z = 0; z < p.batch; ++z)
+          for (int y = 0; y < s_; ++y)
+            for (int i = 0; i < T1; ++i) {
+              const int per = cdiv(kt[i], s_);
+              const int mine = (kt[i] - y * per < per ? kt[i] - y * per : per);
+              const double t = (mine > 0 ? mine : 0) * 2.1 + 3.0 + (s_ > 1 ? 6.0 : 0.0);
+              int best = 0;
+              for (int q = 1; q < sms; ++q) if (busy[q] < busy[best]) best = q;
+              busy[best] += t;
+            }
+        double mx = 0.0;
+        for (int i = 0; i < sms; ++i) if (busy[i] > mx) mx = busy[i];
+        return mx;
       };
-      double best = model(1);
+      double best = makespan(1);
       int best_s = 1;
-      for (int s = 2; s <= 8; ++s) {
-        if (kt_min / s < 16 || (size_t)(T * s) > cap || T > CNT_SLOTS) break;
-        const double cost = model(s);
-        if (cost < 0.97 * best) { best = cost; best_s = s; }
+      int kt_max = 0;
+      for (int i = 0; i < T1; ++i) if (kt[i] > kt_max) kt_max = kt[i];
+      for (int s_ = 2; s_ <= 6; ++s_) {
+        if (kt_max / s_ < 12 || (size_t)(T * s_) > cap) break;
+        const double c = makespan(s_);
+        if (c < 0.97 * best) { best = c; best_s = s_; }
+      }
+      if ((size_t)(T * best_s) > cap) best_s = 1;
+      if (cache_n < 64) {
+        cache_key[cache_n] = PlanKey{p.M, p.N, p.K, p.kmode, (int)lower, p.batch};
+        cache_val[cache_n++] = best_s;
       }
       if (best_s > 1) {
         p.splitk = best_s;
@@ -161,6 +208,8 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
     }
   }
   if (small) return dispatch<CfgSmall>(la, lb, ef, p, stream);
+  static const int big_bk = getenv("GPINV_BIG_BK") ? atoi(getenv("GPINV_BIG_BK")) : 16;
+  if (big_bk == 32 || p.force_cfg == 3) return dispatch<CfgBig32>(la, lb, ef, p, stream);
   return dispatch<CfgBig>(la, lb, ef, p, stream);
 }
 

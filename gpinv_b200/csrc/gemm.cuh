@@ -58,7 +58,7 @@ struct GemmParams {
   int kmode;   // 0 full | 1: k < n0+BN | 2: k >= n0 | 3: k < m0+BM | 4: k >= m0 | 5: n0 <= k < m0+BM
   int splitk;  // >= 1
   int tiles_m, tiles_n;
-  int force_cfg;  // 0 auto | 1 big (128x128) | 2 small (64x64)
+  int force_cfg;  // 0 auto | 1 big (128x128) | 2 small (64x64) | 3 big with BK=32
   // Workspace split-K (wave-quantisation fix): when splitk > 1 and the epilogue is not the
   // atomic one, every k-slice CTA stores its partial tile to `ws`, takes a ticket on the tile's
   // counter, and the LAST arriver sums the slices in fixed order (deterministic) and runs the
@@ -72,10 +72,10 @@ struct GemmParams {
   long long strideA, strideB, strideO, strideCin;
 };
 
-template <int TM_, int TN_, int WM_, int WN_, int STAGES_, int MINB_>
+template <int TM_, int TN_, int WM_, int WN_, int STAGES_, int MINB_, int BK_ = 16>
 struct GemmCfg {
   static constexpr int TM = TM_, TN = TN_, WM = WM_, WN = WN_;   // DMMA tiles per warp, warps per CTA
-  static constexpr int BM = WM * TM * 8, BN = WN * TN * 8, BK = 16;
+  static constexpr int BM = WM * TM * 8, BN = WN * TN * 8, BK = BK_;
   static constexpr int THREADS = WM * WN * 32;
   static constexpr int STAGES = STAGES_;
   static constexpr int MINB = MINB_;
@@ -88,22 +88,65 @@ struct GemmCfg {
 };
 // 128x128 tile, 8 warps, warp tile 64x32, 4 stages, 160 KB smem, 1 CTA/SM: the throughput config
 using CfgBig = GemmCfg<8, 4, 2, 4, 4, 1>;
+// same tile with BK = 32 and 3 stages (216 KB smem): half as many barriers per flop
+using CfgBig32 = GemmCfg<8, 4, 2, 4, 3, 1, 32>;
 // 64x64 tile, 4 warps, warp tile 32x32, 3 stages, 60 KB smem, 3 CTAs/SM: small / short-K problems
 using CfgSmall = GemmCfg<4, 4, 2, 2, 3, 3>;
 
-template <int LAYOUT, int ROWS, int THREADS>
+// Tile decode (heavy tiles first so the hardware block scheduler balances the tail) and k-range
+// of a tile.  Shared by the kernel and by the host-side split planner, which must agree.
+__host__ __device__ __forceinline__ void gemm_decode_tile(int idx, int tiles_m, int tiles_n, int kmode,
+                                                          bool lower, int& tm, int& tn) {
+  if (lower && kmode == 5) {
+    // work grows with the distance from the diagonal: enumerate far diagonals first
+    int d = tiles_m - 1, rem = idx;
+    while (rem >= tiles_m - d) { rem -= tiles_m - d; --d; }
+    tn = rem;
+    tm = rem + d;
+  } else if (lower) {
+    int r = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+    while (r * (r + 1) / 2 > idx) --r;
+    tm = r;
+    tn = idx - r * (r + 1) / 2;
+  } else if (kmode == 1) {
+    tn = tiles_n - 1 - idx / tiles_m;
+    tm = idx % tiles_m;
+  } else if (kmode == 3) {
+    tm = tiles_m - 1 - idx / tiles_n;
+    tn = idx % tiles_n;
+  } else if (kmode == 4) {
+    tm = idx / tiles_n;
+    tn = idx % tiles_n;
+  } else {
+    tn = idx / tiles_m;
+    tm = idx % tiles_m;
+  }
+}
+
+__host__ __device__ __forceinline__ void gemm_krange(int kmode, int K, int m0, int n0, int BM, int BN,
+                                                     int BK, int& kb, int& ke) {
+  kb = 0;
+  ke = K;
+  if (kmode == 1) ke = (K < n0 + BN) ? K : n0 + BN;
+  else if (kmode == 2) kb = (n0 / BK) * BK;
+  else if (kmode == 3) ke = (K < m0 + BM) ? K : m0 + BM;
+  else if (kmode == 4) kb = (m0 / BK) * BK;
+  else if (kmode == 5) { kb = (n0 / BK) * BK; ke = (K < m0 + BM) ? K : m0 + BM; }
+}
+
+template <int LAYOUT, int ROWS, int THREADS, int BK>
 __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restrict__ g, int ld,
                                                int r0, int k0, int Rmax, int Kmax, int vec,
                                                int tid) {
-  constexpr int BK = 16;
   constexpr int LDK = BK + 4;
   constexpr int LDM = ROWS + 4;
   if (LAYOUT == LK) {
     if (vec) {
 #pragma unroll
-      for (int c = 0; c < ROWS * 8 / THREADS; ++c) {
+      for (int c = 0; c < ROWS * (BK / 2) / THREADS; ++c) {
         const int id = tid + c * THREADS;
-        const int row = id >> 3, kc = (id & 7) * 2;
+        const int row = id / (BK / 2), kc = (id % (BK / 2)) * 2;
         const int gr = r0 + row, gk = k0 + kc;
         int valid = (gr < Rmax) ? min(max(Kmax - gk, 0), 2) : 0;
         const double* src = valid ? g + (size_t)gr * ld + gk : g;
@@ -111,9 +154,9 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < ROWS * 16 / THREADS; ++c) {
+      for (int c = 0; c < ROWS * BK / THREADS; ++c) {
         const int id = tid + c * THREADS;
-        const int row = id >> 4, k = id & 15;
+        const int row = id / BK, k = id % BK;
         const int gr = r0 + row, gk = k0 + k;
         const bool ok = (gr < Rmax) && (gk < Kmax);
         const double* src = ok ? g + (size_t)gr * ld + gk : g;
@@ -123,7 +166,7 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
   } else {
     if (vec) {
 #pragma unroll
-      for (int c = 0; c < ROWS * 8 / THREADS; ++c) {
+      for (int c = 0; c < (ROWS / 2) * BK / THREADS; ++c) {
         const int id = tid + c * THREADS;
         const int k = id / (ROWS / 2), rc = (id % (ROWS / 2)) * 2;
         const int gr = r0 + rc, gk = k0 + k;
@@ -133,7 +176,7 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < ROWS * 16 / THREADS; ++c) {
+      for (int c = 0; c < ROWS * BK / THREADS; ++c) {
         const int id = tid + c * THREADS;
         const int k = id / ROWS, r = id % ROWS;
         const int gr = r0 + r, gk = k0 + k;
@@ -144,6 +187,72 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
     }
   }
 }
+
+// Per-thread precomputed state for the 16-byte cp.async path: pointers, shared-memory offsets and
+// row validity are fixed for the whole k loop; per k-tile only the k offset and the k-tail clamp
+// change.  (The 8-byte fallback for unaligned operands keeps using gemm_load_tile.)
+template <int LAYOUT, int ROWS, int THREADS, int BK>
+struct TileLoader {
+  static constexpr int CPR = BK / 2;                        // 16-byte chunks per k-contiguous row
+  static constexpr int NCH = ROWS * CPR / THREADS;          // chunks per thread per tile
+  static constexpr int LDK = BK + 4, LDM = ROWS + 4;
+  const double* ptr;    // first chunk of this thread at k = 0
+  long long step;       // element stride between this thread's consecutive chunks
+  int soff, sstep;      // shared-memory offset of the first chunk / stride between chunks
+  int kfix;             // LK: k offset inside the tile (kc); LMN: first k row (k)
+  int rbytes;           // LMN: valid bytes along the row index (0, 8, 16)
+  unsigned rowmask;     // LK: bit c set when chunk c's row is inside the matrix
+  int ld;
+
+  __device__ __forceinline__ void init(const double* g, int ld_, int r0, int Rmax, int tid) {
+    ld = ld_;
+    if (LAYOUT == LK) {
+      const int row = tid / CPR, kc = (tid % CPR) * 2;
+      constexpr int RPP = THREADS / CPR;                   // rows covered per pass
+      ptr = g + (size_t)(r0 + row) * ld + kc;
+      step = (long long)RPP * ld;
+      soff = row * LDK + kc;
+      sstep = RPP * LDK;
+      kfix = kc;
+      rowmask = 0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) rowmask |= (r0 + row + c * RPP < Rmax) ? (1u << c) : 0u;
+      rbytes = 0;
+    } else {
+      constexpr int HALF = ROWS / 2;
+      constexpr int KPP = THREADS / HALF;                  // k rows covered per pass
+      const int k = tid / HALF, rc = (tid % HALF) * 2;
+      ptr = g + (size_t)k * ld + r0 + rc;
+      step = (long long)KPP * ld;
+      soff = k * LDM + rc;
+      sstep = KPP * LDM;
+      kfix = k;
+      rbytes = min(max(Rmax - (r0 + rc), 0), 2) * 8;
+      rowmask = 0;
+    }
+  }
+
+  // copy the tile whose first k index is k0 (global k limit ke) into stage buffer s
+  __device__ __forceinline__ void load(double* s, const double* g, int k0, int ke) const {
+    if (LAYOUT == LK) {
+      const int kbytes = min(max(ke - (k0 + kfix), 0), 2) * 8;
+      const double* p0 = ptr + k0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int bytes = ((rowmask >> c) & 1u) ? kbytes : 0;
+        cp_async16(s + soff + c * sstep, bytes ? p0 + c * step : g, bytes);
+      }
+    } else {
+      constexpr int KPP = THREADS / (ROWS / 2);
+      const double* p0 = ptr + (size_t)k0 * ld;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int bytes = (k0 + kfix + c * KPP < ke) ? rbytes : 0;
+        cp_async16(s + soff + c * sstep, bytes ? p0 + c * step : g, bytes);
+      }
+    }
+  }
+};
 
 template <class Cfg, int LA, int LB, unsigned EF>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(const GemmParams pin) {
@@ -165,45 +274,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(cons
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
 
-  // ---- tile decode (heavy tiles first so the hardware scheduler balances the tail) ----
+  // ---- tile decode and k range ----
   int tm, tn;
-  {
-    const int idx = blockIdx.x;
-    if ((EF & EF_LOWER) && p.kmode == 5) {
-      // work grows with the distance from the diagonal: enumerate far diagonals first
-      int d = p.tiles_m - 1, rem = idx;
-      while (rem >= p.tiles_m - d) { rem -= p.tiles_m - d; --d; }
-      tn = rem;
-      tm = rem + d;
-    } else if (EF & EF_LOWER) {
-      int r = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
-      while ((r + 1) * (r + 2) / 2 <= idx) ++r;
-      while (r * (r + 1) / 2 > idx) --r;
-      tm = r;
-      tn = idx - r * (r + 1) / 2;
-    } else if (p.kmode == 1) {
-      tn = p.tiles_n - 1 - idx / p.tiles_m;
-      tm = idx % p.tiles_m;
-    } else if (p.kmode == 3) {
-      tm = p.tiles_m - 1 - idx / p.tiles_n;
-      tn = idx % p.tiles_n;
-    } else if (p.kmode == 4) {
-      tm = idx / p.tiles_n;
-      tn = idx % p.tiles_n;
-    } else {
-      tn = idx / p.tiles_m;
-      tm = idx % p.tiles_m;
-    }
-  }
+  gemm_decode_tile(blockIdx.x, p.tiles_m, p.tiles_n, p.kmode, (EF & EF_LOWER) != 0, tm, tn);
   const int m0 = tm * BM, n0 = tn * BN;
-
-  // ---- k range ----
-  int kb = 0, ke = p.K;
-  if (p.kmode == 1) ke = min(p.K, n0 + BN);
-  else if (p.kmode == 2) kb = (n0 / BK) * BK;
-  else if (p.kmode == 3) ke = min(p.K, m0 + BM);
-  else if (p.kmode == 4) kb = (m0 / BK) * BK;
-  else if (p.kmode == 5) { kb = (n0 / BK) * BK; ke = min(p.K, m0 + BM); }
+  int kb, ke;
+  gemm_krange(p.kmode, p.K, m0, n0, BM, BN, BK, kb, ke);
   int ktiles = (ke > kb) ? (ke - kb + BK - 1) / BK : 0;
   if (p.splitk > 1) {
     const int per = (ktiles + p.splitk - 1) / p.splitk;
@@ -221,13 +297,19 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(cons
     for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // ---- pipeline prologue ----
+  TileLoader<LA, BM, THREADS, BK> ldA;
+  TileLoader<LB, BN, THREADS, BK> ldB;
+  ldA.init(p.A, p.lda, m0, p.M, tid);
+  ldB.init(p.B, p.ldb, n0, p.N, tid);
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < ktiles) {
       double* sA = smem + s * STAGE_ELEMS;
       double* sB = sA + A_ELEMS;
-      gemm_load_tile<LA, BM, THREADS>(sA, p.A, p.lda, m0, kb + s * BK, p.M, ke, p.vecA, tid);
-      gemm_load_tile<LB, BN, THREADS>(sB, p.B, p.ldb, n0, kb + s * BK, p.N, ke, p.vecB, tid);
+      if (p.vecA) ldA.load(sA, p.A, kb + s * BK, ke);
+      else gemm_load_tile<LA, BM, THREADS, BK>(sA, p.A, p.lda, m0, kb + s * BK, p.M, ke, 0, tid);
+      if (p.vecB) ldB.load(sB, p.B, kb + s * BK, ke);
+      else gemm_load_tile<LB, BN, THREADS, BK>(sB, p.B, p.ldb, n0, kb + s * BK, p.N, ke, 0, tid);
     }
     cp_async_commit();
   }
@@ -248,8 +330,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(cons
       if (nk < ktiles) {
         double* sA = smem + (nk % STAGES) * STAGE_ELEMS;
         double* sB = sA + A_ELEMS;
-        gemm_load_tile<LA, BM, THREADS>(sA, p.A, p.lda, m0, kb + nk * BK, p.M, ke, p.vecA, tid);
-        gemm_load_tile<LB, BN, THREADS>(sB, p.B, p.ldb, n0, kb + nk * BK, p.N, ke, p.vecB, tid);
+        if (p.vecA) ldA.load(sA, p.A, kb + nk * BK, ke);
+        else gemm_load_tile<LA, BM, THREADS, BK>(sA, p.A, p.lda, m0, kb + nk * BK, p.M, ke, 0, tid);
+        if (p.vecB) ldB.load(sB, p.B, kb + nk * BK, ke);
+        else gemm_load_tile<LB, BN, THREADS, BK>(sB, p.B, p.ldb, n0, kb + nk * BK, p.N, ke, 0, tid);
       }
       cp_async_commit();
     }

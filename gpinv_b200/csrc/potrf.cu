@@ -713,7 +713,7 @@ int potrf_bwd_inv_f64(const double* L, int ldl, double* Ab, int ldab, int n, dou
   {
     GemmParams p = {};
     p.A = L; p.lda = ldl; p.B = Ab; p.ldb = ldab; p.M = n; p.N = n; p.K = n;
-    p.alpha = 1.0; p.out = P; p.ldo = n; p.kmode = 4; p.splitk = 1;
+    p.alpha = 1.0; p.out = P; p.ldo = n; p.kmode = 4; p.splitk = 1; p.allow_split = 1;
     rc = gemm_launch(LMN, LMN, EF_BETA | EF_LOWER, p, st);
     if (rc) return rc;
     scale_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(P, n, n, 0.5);
@@ -723,7 +723,7 @@ int potrf_bwd_inv_f64(const double* L, int ldl, double* Ab, int ldab, int n, dou
   {
     GemmParams p = {};
     p.A = P; p.lda = n; p.B = W; p.ldb = n; p.M = n; p.N = n; p.K = n;
-    p.alpha = 1.0; p.out = T1; p.ldo = n; p.kmode = 5; p.splitk = 1;
+    p.alpha = 1.0; p.out = T1; p.ldo = n; p.kmode = 5; p.splitk = 1; p.allow_split = 1;
     rc = gemm_launch(LK, LMN, EF_BETA | EF_LOWER, p, st);
     if (rc) return rc;
   }
@@ -731,7 +731,7 @@ int potrf_bwd_inv_f64(const double* L, int ldl, double* Ab, int ldab, int n, dou
   {
     GemmParams p = {};
     p.A = W; p.lda = n; p.B = T1; p.ldb = n; p.M = n; p.N = n; p.K = n;
-    p.alpha = 0.5; p.out = Ab; p.ldo = ldab; p.kmode = 4; p.splitk = 1;
+    p.alpha = 0.5; p.out = Ab; p.ldo = ldab; p.kmode = 4; p.splitk = 1; p.allow_split = 1;
     rc = gemm_launch(LMN, LMN, EF_BETA | EF_LOWER, p, st);
     if (rc) return rc;
     p.A = T1; p.B = W; p.beta = 1.0; p.Cin = Ab; p.ldcin = ldab;

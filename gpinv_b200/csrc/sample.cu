@@ -231,7 +231,7 @@ int sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
       p.colvec = q_mu + (size_t)r * n;
       p.out = U + r * sn; p.ldo = n;
       p.sumsq = kl_out + 2;
-      p.kmode = 1; p.splitk = 1;
+      p.kmode = 1; p.splitk = 1; p.allow_split = 1;
       rc = gemm_launch(LK, LK, EF_COLVEC | EF_SUMSQ, p, st);
       if (rc) return rc;
     }
@@ -243,7 +243,7 @@ int sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
     p.colvec = mean + (size_t)r * n;
     p.out = F ? F + r * sn : nullptr; p.ldo = n;
     p.out2 = expF ? expF + r * sn : nullptr; p.ldo2 = n;
-    p.kmode = 1; p.splitk = 1;
+    p.kmode = 1; p.splitk = 1; p.allow_split = 1;
     rc = gemm_launch(LK, LK, expF ? (EF_COLVEC | EF_EXP2) : EF_COLVEC, p, st);
     if (rc) return rc;
   }
@@ -287,7 +287,7 @@ int sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
       p.Cin = U + r * sn; p.ldcin = n;
       p.out = Ubar + r * sn; p.ldo = n;
       p.colsum = qmu_bar + (size_t)r * n;
-      p.kmode = 2; p.splitk = 1;
+      p.kmode = 2; p.splitk = 1; p.allow_split = 1;
       rc = gemm_launch(LK, LMN, EF_BETA | EF_COLSUM, p, st);
       if (rc) return rc;
     }

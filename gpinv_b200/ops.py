@@ -141,6 +141,7 @@ def potrf(K: Tensor) -> Tuple[Tensor, Tensor]:
 def potrf_bwd(L: Tensor, Lbar: Tensor) -> Tensor:
     """Symmetric dObj/dK from dObj/dL (blocked reverse sweep)."""
     L = _chk(L, "L")
+    ensure_workspace(L.device)
     Ab = _chk(Lbar, "Lbar").clone()
     n = L.shape[0]
     lib = _capi.lib()
@@ -222,6 +223,7 @@ def stvgp_sample(Lc: Tensor, sqrt_v: Tensor, Q: Tensor, q_mu: Tensor, mean: Tens
     mean [R,n], E [R,S,n]."""
     Lc = _chk(Lc, "Lc"); sqrt_v = _chk(sqrt_v, "sqrt_v"); Q = _chk(Q, "Q")
     q_mu = _chk(q_mu, "q_mu"); mean = _chk(mean, "mean"); E = _chk(E, "E")
+    ensure_workspace(E.device)
     R, S, n = E.shape
     U = torch.empty_like(E)
     F = torch.empty_like(E)
