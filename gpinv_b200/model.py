@@ -12,7 +12,11 @@ nothing synchronises).
 """
 from __future__ import annotations
 
+import os
 import sys
+import threading
+import time
+import weakref
 
 import numpy as np
 import torch
@@ -32,6 +36,7 @@ class Model(Parameterized):
         self._pending_infos = []
         self.dist = None            # set by gpinv_b200.dist.attach()
         self._pinned = {}
+        self._out_pool = []
         self._use_graph = False
         self._graphs = {}
 
@@ -128,12 +133,14 @@ class Model(Parameterized):
         x = np.ascontiguousarray(x, dtype=np.float64)
         dev = default_device()
         n = x.size
-        pin = self._pinned.get(n)
-        if pin is None:
-            pin = (torch.empty(n, dtype=torch.float64).pin_memory(),
-                   torch.empty(n + 1, dtype=torch.float64).pin_memory())
-            self._pinned = {n: pin}
-        hin, hout = pin
+        hin = self._pinned.get(n)
+        if hin is None:
+            hin = torch.empty(n, dtype=torch.float64).pin_memory()
+            self._pinned = {n: hin}
+            self._out_pool = []
+        hout, finish = self._result_buffer(n)
+        if n >= self.OVERLAP_MIN and self.dist is None and not self._use_graph:
+            return self._objective_host_overlapped(x, hin, hout, finish, dev, **kw)
         # torch's CPU copy is multi-threaded; a plain numpy assignment of 134 MB is not
         hin.copy_(torch.from_numpy(x))
         xd = hin.to(dev, non_blocking=True)
@@ -142,9 +149,198 @@ class Model(Parameterized):
         hout[1:].copy_(g, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self._check_infos()
-        grad = np.empty(n, dtype=np.float64)
-        torch.from_numpy(grad).copy_(hout[1:])
-        return float(hout[0].item()), grad
+        return finish()
+
+    POOL_MIN = 1 << 16        # below this many entries the gradient is copied into a fresh array
+
+    def _result_buffer(self, n):
+        """Pinned [1+n] buffer that receives (-f, -df/dx), and the function that turns it into the
+        returned ``(float, ndarray)``.  For large states the ndarray is a *view* of the pinned
+        buffer (a second 134 MB host copy would cost as much as the D2H transfer itself); a buffer
+        goes back into circulation only after every array derived from it has been released,
+        which a weak reference to the view's base detects, so results the caller still holds are
+        never overwritten."""
+        if n < self.POOL_MIN:
+            if getattr(self, "_small_out", None) is None or self._small_out.numel() != n + 1:
+                self._small_out = torch.empty(n + 1, dtype=torch.float64).pin_memory()
+            hout = self._small_out
+
+            def finish():
+                return float(hout[0].item()), hout[1:].numpy().copy()
+            return hout, finish
+        pool = self._out_pool
+        ent = None
+        for e in pool:
+            if e[0].numel() == n + 1 and (e[1] is None or e[1]() is None):
+                ent = e
+                break
+        if ent is None:
+            # page-locking 134 MB takes ~100 ms: allocate two at once the first time, because an
+            # optimiser typically still holds the previous gradient while it asks for the next
+            for _ in range(2 if not pool else 1):
+                ent = [torch.empty(n + 1, dtype=torch.float64).pin_memory(), None]
+                pool.append(ent)
+        hout = ent[0]
+
+        def finish():
+            base = hout.numpy()           # keeps ``hout``'s storage alive through its own reference
+            ent[1] = weakref.ref(base)
+            return float(base[0]), base[1:]
+        return hout, finish
+
+    OVERLAP_MIN = 1 << 21     # elements of x above which the host path pipelines its transfers
+
+    def _objective_host_overlapped(self, x, hin, hout, finish, dev, **kw):
+        """Host API for large states (the 134 MB x / gradient of the headline config): the
+        largest parameter block (q_sqrt) is staged and uploaded by a helper thread in chunks while
+        the kernel build and the Cholesky already run, and its gradient — ready as soon as the
+        sampling stage's reverse pass is done — is downloaded on a copy stream while the Cholesky
+        reverse sweep still runs."""
+        trace = [] if os.environ.get("GPINV_E2E_TRACE") else None
+
+        def tr(name):
+            if trace is not None:
+                trace.append((name, time.perf_counter()))
+        tr("start")
+        self._prepare()
+        n = x.size
+        params = [p for p in self.all_params() if not p.fixed]
+        offs, o = [], 0
+        for p in params:
+            offs.append((o, o + p.size))
+            o += p.size
+        big = max(range(len(params)), key=lambda i: params[i].size)
+        b0, b1 = offs[big]
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        cs = self._copy_stream
+        # the big block lives in its own allocation: the upload thread writes it in place while
+        # autograd already holds (version-counted) views of the other blocks
+        xd = torch.empty(n - (b1 - b0), dtype=torch.float64, device=dev)
+        xt = torch.from_numpy(x)
+        nq = params[big]._tril_rows
+        tri = nq is not None and nq * nq == b1 - b0 and nq >= 512
+        ready = threading.Event()
+        state = {"h2d": 0}
+
+        if tri:
+            # Only tril(q_sqrt) is read by the model: stage, transfer and scatter the lower
+            # trapezoid of each block of rows (0.53 n^2 entries instead of n^2).
+            xbig = torch.zeros(b1 - b0, dtype=torch.float64, device=dev)
+            nblk = 16
+            rb = -(-nq // nblk)
+            total = sum((min(nq, r0 + rb) - r0) * min(nq, r0 + rb) for r0 in range(0, nq, rb))
+            dstage = torch.empty(total, dtype=torch.float64, device=dev)
+            src2, dst2 = xt[b0:b1].view(nq, nq), xbig.view(nq, nq)
+
+            def upload_chunks():
+                o = 0
+                for r0 in range(0, nq, rb):
+                    r1 = min(nq, r0 + rb)
+                    cnt = (r1 - r0) * r1
+                    st = hin[b0 + o:b0 + o + cnt].view(r1 - r0, r1)
+                    st.copy_(src2[r0:r1, :r1])                      # threaded strided host copy
+                    dv = dstage[o:o + cnt].view(r1 - r0, r1)
+                    dv.copy_(st, non_blocking=True)                 # contiguous DMA
+                    dst2[r0:r1, :r1].copy_(dv)                      # strided scatter on the device
+                    o += cnt
+                    state["h2d"] += 8 * cnt
+        else:
+            xbig = torch.empty(b1 - b0, dtype=torch.float64, device=dev)
+
+            def upload_chunks():
+                nch = 4
+                step = -(-(b1 - b0) // nch)
+                for c in range(nch):
+                    a, b = b0 + c * step, min(b1, b0 + (c + 1) * step)
+                    if b > a:
+                        hin[a:b].copy_(xt[a:b])
+                        xbig[a - b0:b - b0].copy_(hin[a:b], non_blocking=True)
+                        state["h2d"] += 8 * (b - a)
+
+        def upload():
+            try:
+                with torch.cuda.stream(cs):
+                    upload_chunks()
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                state["ev"] = ev
+                tr("upload_issued")
+            except BaseException as e:   # pragma: no cover
+                state["err"] = e
+            finally:
+                ready.set()
+
+        cs.wait_stream(cur)       # the copy stream starts after xbig's allocation / zero fill
+        th = threading.Thread(target=upload, daemon=True)
+        th.start()
+        # head and tail (everything but the big block): small, on the compute stream
+        for a, b, d in ((0, b0, 0), (b1, n, b0)):
+            if b > a:
+                hin[a:b].copy_(xt[a:b])
+                xd[d:d + b - a].copy_(hin[a:b], non_blocking=True)
+                state["h2d"] += 8 * (b - a)
+
+        def wait_big():
+            tr("wait_big")
+            ready.wait()
+            tr("wait_big_done")
+            if "err" in state:
+                raise state["err"]
+            torch.cuda.current_stream().wait_event(state["ev"])
+
+        keep = {}
+
+        def big_grad_hook(g):
+            # runs on the autograd thread as soon as d(-f)/d(big block) exists
+            tr("big_grad_hook")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            gf = g.reshape(-1)
+            keep["g"] = gf
+            with torch.cuda.stream(cs):
+                cs.wait_event(ev)
+                hout[1 + b0:1 + b1].copy_(gf, non_blocking=True)
+            keep["done"] = True
+
+        leaves = self.make_tensors(xd, override={big: xbig})
+        params[big]._before_use = wait_big
+        leaves[big].register_hook(big_grad_hook)
+        self._pending_infos = []
+        try:
+            with self.tensor_mode():
+                f = self.build_likelihood(**kw)
+                prior = self.build_prior()
+                if prior is not None:
+                    f = f + prior
+            nf = -f.reshape(())
+            tr("forward_issued")
+            grads = torch.autograd.grad(nf, leaves, allow_unused=True)
+        finally:
+            params[big]._before_use = None
+            self.clear_tensors()
+            th.join()
+        hout[:1].copy_(nf.detach().reshape(1), non_blocking=True)
+        for i, (g, (a, b)) in enumerate(zip(grads, offs)):
+            if i == big and keep.get("done"):
+                continue
+            if g is None:
+                hout[1 + a:1 + b].zero_()
+            else:
+                hout[1 + a:1 + b].copy_(g.reshape(-1), non_blocking=True)
+        tr("grads_issued")
+        cur.synchronize()
+        cs.synchronize()
+        tr("synced")
+        self._check_infos()
+        out = finish()
+        self._last_h2d_bytes = state["h2d"]
+        tr("done")
+        if trace is not None:
+            print("e2e-trace " + " ".join("%s=%.2f" % (k, 1e3 * (v - trace[0][1])) for k, v in trace),
+                  file=sys.stderr)
+        return out
 
     def compute_log_likelihood(self, **kw):
         x = torch.as_tensor(self.get_free_state()).to(default_device())

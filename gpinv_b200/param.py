@@ -76,6 +76,8 @@ class Param(Parentable):
         self.prior = None
         self._tensor = None
         self._free_leaf = None
+        self._before_use = None     # optional callable run once before the tensor is first read
+        self._tril_rows = None      # n if the value is one row-major [n,n] matrix read as tril() only
 
     @property
     def value(self):
@@ -165,6 +167,9 @@ class Parameterized(Parentable):
                     return o.tensor()
                 if o._tensor is None:
                     raise RuntimeError("Param %s has no tensor (not inside an objective evaluation)" % key)
+                if o._before_use is not None:
+                    cb, o._before_use = o._before_use, None
+                    cb()
                 return o._tensor
         return o
 
@@ -243,10 +248,13 @@ class Parameterized(Parentable):
     # alias so that code written against the reference keeps working
     tf_mode = tensor_mode
 
-    def make_tensors(self, x: torch.Tensor):
+    def make_tensors(self, x: torch.Tensor, override=None):
         """Bind every Param to a tensor derived from the free-state vector ``x`` (device,
         fp64).  Returns the list of leaf tensors (one per non-fixed Param, views of ``x``'s
-        storage) whose gradients, concatenated, form d/dx."""
+        storage) whose gradients, concatenated, form d/dx.  ``override`` maps the index of a
+        free Param (position in the returned list) to a separately allocated flat tensor that
+        holds its block; ``x`` then packs only the remaining blocks (used by the pipelined host
+        path, whose upload thread fills that block while other leaves are already in use)."""
         leaves = []
         off = 0
         for p in self.all_params():
@@ -255,11 +263,17 @@ class Parameterized(Parentable):
                 p._free_leaf = None
                 continue
             n = p.size
-            leaf = x[off:off + n].detach().view(p.shape).requires_grad_(True)
+            if override and len(leaves) in override:
+                src = override[len(leaves)]
+                if src.numel() != n:
+                    raise ValueError("override block has %d entries, the Param has %d" % (src.numel(), n))
+            else:
+                src = x[off:off + n]
+                off += n
+            leaf = src.detach().view(p.shape).requires_grad_(True)
             p._free_leaf = leaf
             p._tensor = p.transform.torch_forward(leaf)
             leaves.append(leaf)
-            off += n
         if off != x.numel():
             raise ValueError("state vector has %d entries, the model has %d free parameters" % (x.numel(), off))
         return leaves

@@ -46,6 +46,10 @@ class StVGP(GPModel):
         else:
             q_sqrt = np.array([np.eye(self.num_data) for _ in range(self.num_latent)]).swapaxes(0, 2)
             self.q_sqrt = Param(q_sqrt)
+            if self.num_latent == 1:
+                # only the lower triangle of each [n,n] slice is ever read (band_part,
+                # GPinv/stvgp.py:157): lets the host API upload the lower trapezoids only
+                self.q_sqrt._tril_rows = self.num_data
 
     def _prepare(self):
         """GPinv/stvgp.py:76-94: re-create the variational parameters when X changed size."""

@@ -290,3 +290,23 @@ def test_cuda_graph_replay_matches_eager():
     fg, gg = mc._objective(xc)
     fg, gg = mc._objective(xc)
     assert abs(fg - fe) <= 1e-11 * abs(fe) and rel_err(gg, ge) <= 1e-11
+
+
+@pytest.mark.parametrize("n", [400, 640])      # 640: lower-trapezoid upload of q_sqrt (n >= 512)
+def test_overlapped_host_path_matches_plain_host_path(n):
+    """The pipelined host API (chunked upload thread + early gradient download) must return what
+    the plain path returns, for a state that changes from call to call (a stale buffer or a
+    copy racing the kernels would show as an O(1) error, not as summation-order noise)."""
+    m = make_abel_stvgp(n, 300, 16)
+    m.kern.lengthscales = 0.3
+    eps = np.random.RandomState(3).randn(1, 16, n)
+    xs = [perturbed_state(m, 0.02, seed=s) for s in (1, 2, 3)]
+    plain = [m._objective(x, eps=eps) for x in xs]
+    m.OVERLAP_MIN = 1000
+    for x, (f0, g0) in zip(xs, plain):
+        f1, g1 = m._objective(x, eps=eps)
+        g1 = g1.copy()
+        assert abs(f1 - f0) <= 1e-10 * abs(f0) and rel_err(g1, g0) <= 1e-10
+        # upper-triangular entries of q_sqrt still get an exactly-zero gradient
+        gq = g1[-n * n:].reshape(n, n)
+        assert np.all(gq[np.triu_indices(n, 1)] == 0.0)
