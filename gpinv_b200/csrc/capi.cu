@@ -22,6 +22,8 @@ int potrf_bwd_f64(const double*, int, double*, int, int, double*, cudaStream_t);
 int trsm_rlt_f64(const double*, int, double*, int, int, int, cudaStream_t);
 size_t potrf_bwd_inv_ws_bytes(int);
 int potrf_bwd_inv_f64(const double*, int, double*, int, int, double*, cudaStream_t);
+int potrf_bwd_hybrid_f64(const double*, int, double*, int, int, double*, cudaStream_t);
+int potrf_bwd_hybrid_block();
 int tril_unpack_f64(const double*, double*, int, int, cudaStream_t);
 int tril_pack_f64(const double*, double*, int, int, cudaStream_t);
 int sumsq_f64(const double*, size_t, double*, cudaStream_t);
@@ -78,13 +80,14 @@ int gpinv_potrf_f64(double* A, int n, int lda, int* info, void* stream) {
   return potrf_f64(A, n, lda, info, ST(stream));
 }
 
-static bool use_murray() {
+// GPINV_POTRF_BWD = murray | inv | hybrid (default): which reverse sweep of the Cholesky runs
+static int bwd_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GPINV_POTRF_BWD");
-    v = (e && strcmp(e, "murray") == 0) ? 1 : 0;
+    v = (e && strcmp(e, "murray") == 0) ? 1 : (e && strcmp(e, "inv") == 0) ? 2 : 0;
   }
-  return v == 1;
+  return v;
 }
 
 size_t gpinv_potrf_bwd_ws_bytes(int n) {
@@ -95,7 +98,10 @@ size_t gpinv_potrf_bwd_ws_bytes(int n) {
 int gpinv_potrf_bwd_f64(const double* L, int ldl, double* Abar, int ldab, int n, void* ws,
                         void* stream) {
   if (n <= 0 || ldl < n || ldab < n) return GPINV_ERR_ARG;
-  if (use_murray()) return potrf_bwd_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
+  const int mode = bwd_mode();
+  if (mode == 1) return potrf_bwd_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
+  if (mode == 0 && n > potrf_bwd_hybrid_block())
+    return potrf_bwd_hybrid_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
   return potrf_bwd_inv_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
 }
 

@@ -207,6 +207,10 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
       }
     }
   }
+  static const bool log_gemm = (getenv("GPINV_GEMM_LOG") != nullptr);
+  if (log_gemm)
+    fprintf(stderr, "gemm-log la=%d lb=%d ef=%u M=%d N=%d K=%d kmode=%d splitk=%d batch=%d cfg=%s\n", la, lb, ef,
+            p.M, p.N, p.K, p.kmode, p.splitk, p.batch, small ? "small" : "big");
   if (small) return dispatch<CfgSmall>(la, lb, ef, p, stream);
   static const int big_bk = getenv("GPINV_BIG_BK") ? atoi(getenv("GPINV_BIG_BK")) : 16;
   if (big_bk == 32 || p.force_cfg == 3) return dispatch<CfgBig32>(la, lb, ef, p, stream);

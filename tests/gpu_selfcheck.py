@@ -75,7 +75,7 @@ def spd(n, seed):
 
 
 def check_potrf():
-    for n in (1, 5, 64, 65, 100, 256, 300, 515, 1024, 2048):
+    for n in (1, 5, 64, 65, 100, 256, 300, 515, 1024, 1100, 2048, 2500):   # > 1024: hybrid blocked reverse
         K = spd(n, n)
         Kt = torch.tensor(K, requires_grad=True)
         Lref = torch.linalg.cholesky(Kt)
