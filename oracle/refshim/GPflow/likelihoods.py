@@ -1,0 +1,9 @@
+"""GPflow.likelihoods.Likelihood base (only the class identity is used by the reference)."""
+from .param import Parameterized
+
+
+class Likelihood(Parameterized):
+    def __init__(self):
+        Parameterized.__init__(self)
+        self.scoped_keys.extend(["logp", "variational_expectations", "predict_mean_and_var",
+                                 "predict_density"])

@@ -46,7 +46,38 @@ def build_spec(name):
                     mean=dict(type="stack", mean_list=[dict(type="constant", output_dim=2),
                                                        dict(type="zero", output_dim=1)]),
                     lik=dict(type="spec_abel", A=A, cosT=cosT, lam=lam), num_latent=3)
+    if name == "abel_stvgp_cfg1":          # BASELINE.json configs[0]: N=30, 40 chords, S=10
+        return build_spec("abel_stvgp_n30")
+    if name == "abel_stvgp_n200":          # mid-size: multi-tile GEMMs and a 4-panel Cholesky on the GPU
+        r, z, A, y = _abel(200, 150)
+        return dict(model="stvgp", X=r[:, None], Y=y[:, None],
+                    kern=dict(type="rbf_csym", input_dim=1, output_dim=1, ARD=False),
+                    mean=dict(type="constant", output_dim=1), lik=dict(type="abel", A=A), num_latent=1)
+    if name == "gauss_stvgp_full_klanalytic":
+        spec = build_spec("gauss_stvgp_n40")
+        spec["KL_analytic"] = True
+        return spec
+    if name == "ard_multi_gauss":
+        rng = np.random.RandomState(0)
+        n, R = 24, 3
+        X, Y = rng.rand(n, 2), rng.randn(n, R)
+        return dict(model="stvgp", X=X, Y=Y, kern=dict(type="rbf", input_dim=2, output_dim=R, ARD=True),
+                    mean=dict(type="constant", output_dim=R), lik=dict(type="gaussian"), num_latent=R)
+    if name == "rbf2d_kron_qdiag":
+        rng = np.random.RandomState(0)
+        d1, d2 = np.linspace(0, 1, 4), np.linspace(-1, 1, 5)
+        X = np.array([[a, b] for a in d1 for b in d2])
+        R = 2
+        return dict(model="stvgp", X=X, Y=rng.randn(X.shape[0], R),
+                    kern=dict(type="rbf2d", input_dim=1, output_dim=R, ARD=False, dim1=d1[:, None], dim2=d2[:, None]),
+                    mean=dict(type="zero", output_dim=R), lik=dict(type="gaussian"), num_latent=R, q_diag=True)
     raise KeyError(name)
+
+
+# cases whose fixtures are produced by the reference's own code (oracle/run_reference.py)
+REF_CASES = CASES + ["gauss_stvgp_full_klanalytic", "ard_multi_gauss", "rbf2d_kron_qdiag",
+                     "abel_stvgp_cfg1", "abel_stvgp_n200"]
+REF_SAMPLES = {"abel_stvgp_cfg1": 10, "abel_stvgp_n200": 8}      # default 6
 
 
 def main():

@@ -49,6 +49,41 @@ def spec_from_model(m):
     }
 
 
+def model_from_spec(spec, S=6):
+    """The gpinv_b200 model for an oracle-style plain-dict description (inverse of
+    ``spec_from_model``; used with the reference-executed fixtures tests/golden/ref_*.npz)."""
+    from gpinv_b200 import gpmc, stvgp
+
+    def kern(k):
+        if k["type"] == "stack":
+            return kernels.Stack([kern(s) for s in k["kern_list"]])
+        if k["type"] == "rbf2d":
+            return kronecker.RBF2D(k["input_dim"], k["output_dim"], k["dim1"], k["dim2"], ARD=k["ARD"])
+        cls = {"rbf": kernels.RBF, "rbf_csym": kernels.RBF_csym, "rbf_casym": kernels.RBF_casym}[k["type"]]
+        return cls(k["input_dim"], k["output_dim"], ARD=k["ARD"])
+
+    def mean(m):
+        if m["type"] == "stack":
+            return mean_functions.Stack([mean(s) for s in m["mean_list"]])
+        if m["type"] == "constant":
+            return mean_functions.Constant(m["output_dim"])
+        return mean_functions.Zero(m["output_dim"])
+
+    lk = spec["lik"]
+    if lk["type"] == "abel":
+        lik = likelihoods.AbelLikelihood(lk["A"])
+    elif lk["type"] == "spec_abel":
+        lik = likelihoods.SpecAbelLikelihood(lk["A"], lk["cosT"], lk["lam"])
+    else:
+        lik = likelihoods.Gaussian()
+    if spec["model"] == "gpmc":
+        return gpmc.GPMC(spec["X"], spec["Y"], kern(spec["kern"]), lik, mean(spec["mean"]),
+                         num_latent=spec["num_latent"])
+    return stvgp.StVGP(spec["X"], spec["Y"], kern(spec["kern"]), lik, mean(spec["mean"]),
+                       num_latent=spec["num_latent"], q_diag=spec.get("q_diag", False),
+                       KL_analytic=spec.get("KL_analytic", False), num_samples=S)
+
+
 def abel_data(n, M, seed=0):
     """SURVEY.md 8(d) cfg1/cfg5 generator (notebooks/Abel_inversion.ipynb:115-120,183-185)."""
     r = np.linspace(0, 1., n)
