@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--impl", default="gpinv_b200")
     ap.add_argument("--config", default="cfg5", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch the evaluation eagerly instead of replaying its CUDA graph (1 GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -195,6 +197,8 @@ def main():
     m = build_model(n, M, S)
     if world > 1:
         gdist.attach(m)
+    elif not args.no_graph:
+        m.enable_cuda_graph()       # one captured graph per evaluation (~250 launches), replayed
     x_host = m.get_free_state()
     x = torch.as_tensor(x_host).to(dev)
     eps = torch.randn((1, S, n), dtype=torch.float64, device=dev,

@@ -117,8 +117,11 @@ int gpinv_gemm_f64(int transa, int transb, int m, int n, int k, double alpha, co
   // op(B) is k x n.  'N': B stored k x n (n contiguous -> LMN);  'T': stored n x k (LK).
   const int la = transa ? LMN : LK;
   const int lb = transb ? LK : LMN;
-  return gemm_simple(la, lb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower != 0, 0, 1,
-                     ST(stream));
+  GemmParams p = {};
+  p.A = A; p.B = B; p.M = m; p.N = n; p.K = k; p.lda = lda; p.ldb = ldb;
+  p.alpha = alpha; p.beta = beta; p.Cin = C; p.ldcin = ldc; p.out = C; p.ldo = ldc;
+  p.splitk = 1; p.allow_split = 1;     // the launcher may k-split through the registered workspace
+  return gemm_launch(la, lb, EF_BETA | (lower ? EF_LOWER : 0u), p, ST(stream));
 }
 
 int gpinv_tril_unpack_f64(const double* src, double* dst, int n, int R, void* stream) {

@@ -211,6 +211,25 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
   if (log_gemm)
     fprintf(stderr, "gemm-log la=%d lb=%d ef=%u M=%d N=%d K=%d kmode=%d splitk=%d batch=%d cfg=%s\n", la, lb, ef,
             p.M, p.N, p.K, p.kmode, p.splitk, p.batch, small ? "small" : "big");
+  // ---- k-split for the 64x64 configuration: a few hundred short tiles cannot fill 148 SMs x 3
+  // resident CTAs (e.g. the 1024^3 triangular products of the Cholesky reverse leaves: 136 tiles)
+  if (p.allow_split && !no_split && p.splitk == 1 && !(ef & EF_ATOMIC) && small) {
+    WsReg* w = ws_for_device();
+    const int tm_ = cdiv(p.M, 64), tn_ = cdiv(p.N, 64);
+    const long long T = (long long)(lower ? tm_ * (tm_ + 1) / 2 : tm_ * tn_) * p.batch;
+    const int ktiles = cdiv(p.K, 16);
+    const int slots = 148 * 3;
+    int s_ = (int)(slots / (T > 0 ? T : 1));
+    s_ = min(s_, ktiles / 12);          // >= 12 k-tiles (192 columns of K) per slice
+    s_ = min(s_, 4);
+    const size_t tile_bytes = 64 * 64 * sizeof(double);
+    const size_t cap = (w && w->bytes > CNT_SLOTS * sizeof(int)) ? (w->bytes - CNT_SLOTS * sizeof(int)) / tile_bytes : 0;
+    if (w && s_ >= 2 && T <= CNT_SLOTS && (size_t)(T * s_) <= cap) {
+      p.splitk = s_;
+      p.ws_cnt = static_cast<int*>(w->ptr);
+      p.ws = reinterpret_cast<double*>(static_cast<char*>(w->ptr) + CNT_SLOTS * sizeof(int));
+    }
+  }
   if (small) return dispatch<CfgSmall>(la, lb, ef, p, stream);
   static const int big_bk = getenv("GPINV_BIG_BK") ? atoi(getenv("GPINV_BIG_BK")) : 16;
   if (big_bk == 32 || p.force_cfg == 3) return dispatch<CfgBig32>(la, lb, ef, p, stream);

@@ -90,6 +90,8 @@ struct GemmCfg {
 using CfgBig = GemmCfg<8, 4, 2, 4, 4, 1>;
 // same tile with BK = 32 and 3 stages (216 KB smem): half as many barriers per flop
 using CfgBig32 = GemmCfg<8, 4, 2, 4, 3, 1, 32>;
+// (A 16-warp variant of the 128x128 tile -- warp tile 32x32, 4 warps per scheduler -- was measured
+// and is 0.5-4 % slower on every shape of the evaluation: GemmCfg<4, 4, 4, 4, 4, 1>.)
 // 64x64 tile, 4 warps, warp tile 32x32, 3 stages, 60 KB smem, 3 CTAs/SM: small / short-K problems
 using CfgSmall = GemmCfg<4, 4, 2, 2, 3, 3>;
 

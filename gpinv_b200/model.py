@@ -139,7 +139,9 @@ class Model(Parameterized):
             self._pinned = {n: hin}
             self._out_pool = []
         hout, finish = self._result_buffer(n)
-        if n >= self.OVERLAP_MIN and self.dist is None and not self._use_graph:
+        if n >= self.OVERLAP_MIN:
+            # large states: the transfers are pipelined against the evaluation (eager launches:
+            # the upload must be able to slot in between the Cholesky and the sampling stage)
             return self._objective_host_overlapped(x, hin, hout, finish, dev, **kw)
         # torch's CPU copy is multi-threaded; a plain numpy assignment of 134 MB is not
         hin.copy_(torch.from_numpy(x))
@@ -298,6 +300,12 @@ class Model(Parameterized):
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
             gf = g.reshape(-1)
+            if self.dist is not None:
+                # sum this block over the ranks right away (own all-reduce, same order on every
+                # rank); the small remainder is reduced after the backward pass
+                gf = gf.contiguous()
+                self.dist.all_reduce(gf)
+                ev.record(torch.cuda.current_stream())
             keep["g"] = gf
             with torch.cuda.stream(cs):
                 cs.wait_event(ev)
@@ -313,7 +321,7 @@ class Model(Parameterized):
                 f = self.build_likelihood(**kw)
                 prior = self.build_prior()
                 if prior is not None:
-                    f = f + prior
+                    f = f + (prior if self.dist is None else prior / self.dist.world_size)
             nf = -f.reshape(())
             tr("forward_issued")
             grads = torch.autograd.grad(nf, leaves, allow_unused=True)
@@ -321,14 +329,19 @@ class Model(Parameterized):
             params[big]._before_use = None
             self.clear_tensors()
             th.join()
-        hout[:1].copy_(nf.detach().reshape(1), non_blocking=True)
-        for i, (g, (a, b)) in enumerate(zip(grads, offs)):
-            if i == big and keep.get("done"):
-                continue
-            if g is None:
-                hout[1 + a:1 + b].zero_()
-            else:
-                hout[1 + a:1 + b].copy_(g.reshape(-1), non_blocking=True)
+        rest = [(i, a, b) for i, (a, b) in enumerate(offs) if not (i == big and keep.get("done"))]
+        parts = [nf.detach().reshape(1)]
+        for i, a, b in rest:
+            parts.append(torch.zeros(b - a, dtype=torch.float64, device=dev) if grads[i] is None
+                         else grads[i].reshape(-1))
+        small = torch.cat(parts)
+        if self.dist is not None:
+            self.dist.all_reduce(small)
+        hout[:1].copy_(small[:1], non_blocking=True)
+        o = 1
+        for i, a, b in rest:
+            hout[1 + a:1 + b].copy_(small[o:o + b - a], non_blocking=True)
+            o += b - a
         tr("grads_issued")
         cur.synchronize()
         cs.synchronize()
