@@ -174,6 +174,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # Only the JSON line may reach stdout: NCCL prints its version banner there, so fd 1 is
+    # pointed at stderr for the duration of the run and the line is written to the saved fd.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from gpinv_b200 import dist as gdist
@@ -197,6 +203,9 @@ def main():
     m = build_model(n, M, S)
     if world > 1:
         gdist.attach(m)
+        # torchrun exports OMP_NUM_THREADS=1; the host API stages 134 MB per call with torch's
+        # threaded CPU copy, so give every rank its share of the host cores back
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
     elif not args.no_graph:
         m.enable_cuda_graph()       # one captured graph per evaluation (~250 launches), replayed
     x_host = m.get_free_state()
@@ -327,7 +336,8 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(n, M, S)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -36,6 +36,12 @@ class DistContext(object):
         return buf
 
 
+    def all_reduce_async(self, buf):
+        """Start the sum over ranks and return the work handle (``.wait()`` orders the caller's
+        stream after it)."""
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+
 def attach(model, ctx=None):
     """Make ``model._objective`` evaluate its shard and all-reduce [-f, -grad]."""
     model.dist = ctx if ctx is not None else DistContext()
