@@ -9,6 +9,24 @@ namespace gpinv {
 namespace {
 
 template <class Cfg, int LA, int LB, unsigned EF>
+int launch_persistent(const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_dmma_persistent_kernel<Cfg, LA, LB, EF>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error(cudaGetErrorString(e));
+      return GPINV_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
+template <class Cfg, int LA, int LB, unsigned EF>
 int launch_inst(const GemmParams& p, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
   auto kern = gemm_dmma_kernel<Cfg, LA, LB, EF>;
@@ -95,6 +113,17 @@ int dispatch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) {
   }
   const int ntiles = (ef & EF_LOWER) ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
   dim3 grid(ntiles, p.splitk, p.batch);
+  p.ntiles = ntiles;
+  if (p.max_ctas > 0 && p.splitk == 1 && p.batch == 1 && ntiles > p.max_ctas) {
+    // persistent, CTA-capped instantiations (only the combinations that run beside the
+    // Cholesky panel chain exist)
+    grid.x = p.max_ctas;
+    if (la == LK && lb == LK && ef == (EF_BETA | EF_LOWER))
+      return launch_persistent<Cfg, LK, LK, EF_BETA | EF_LOWER>(p, grid, stream);
+    if (la == LK && lb == LK && ef == (EF_COLVEC | EF_SUMSQ))
+      return launch_persistent<Cfg, LK, LK, EF_COLVEC | EF_SUMSQ>(p, grid, stream);
+    grid.x = ntiles;
+  }
 
   GPINV_GEMM_GENERIC(LK, LK)
   GPINV_GEMM_GENERIC(LK, LMN)
@@ -135,6 +164,7 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
   // with a per-CTA time model and keep the split factor with the smallest makespan.  Fixes wave
   // quantisation (uniform K) and the long-tile imbalance of the triangular products.
   static const bool no_split = (getenv("GPINV_NO_SPLIT") != nullptr);
+  if (p.max_ctas > 0) p.allow_split = 0;
   if (p.allow_split && !no_split && p.splitk == 1 && !(ef & EF_ATOMIC) && !small) {
     WsReg* w = ws_for_device();
     const int tm_ = cdiv(p.M, 128), tn_ = cdiv(p.N, 128);

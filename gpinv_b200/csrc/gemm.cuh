@@ -70,6 +70,12 @@ struct GemmParams {
   // batching over blockIdx.z (element strides; 0 = shared operand)
   int batch;
   long long strideA, strideB, strideO, strideCin;
+  // Persistent mode (max_ctas > 0, splitk == 1, batch == 1): the grid is capped at max_ctas and
+  // every CTA walks the tile list with stride gridDim.x.  Used for GEMMs that run BESIDE a
+  // latency-critical kernel chain on another stream (the look-ahead update of the Cholesky, the
+  // first sampling product): they must leave SMs free instead of flooding the machine.
+  int max_ctas;
+  int ntiles;   // filled by the launcher
 };
 
 template <int TM_, int TN_, int WM_, int WN_, int STAGES_, int MINB_, int BK_ = 16>
@@ -257,11 +263,10 @@ struct TileLoader {
 };
 
 template <class Cfg, int LA, int LB, unsigned EF>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(const GemmParams pin) {
+__device__ __forceinline__ void gemm_tile_body(const GemmParams& pin, const int tile_x, double* smem) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
   constexpr int TM = Cfg::TM, TN = Cfg::TN, LDK = Cfg::LDK, LDMA = Cfg::LDMA, LDMB = Cfg::LDMB;
   constexpr int A_ELEMS = Cfg::A_ELEMS, STAGE_ELEMS = Cfg::STAGE_ELEMS;
-  extern __shared__ __align__(16) double smem[];
   GemmParams p = pin;
   if (p.batch > 1) {
     const long long z = blockIdx.z;
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(cons
 
   // ---- tile decode and k range ----
   int tm, tn;
-  gemm_decode_tile(blockIdx.x, p.tiles_m, p.tiles_n, p.kmode, (EF & EF_LOWER) != 0, tm, tn);
+  gemm_decode_tile(tile_x, p.tiles_m, p.tiles_n, p.kmode, (EF & EF_LOWER) != 0, tm, tn);
   const int m0 = tm * BM, n0 = tn * BN;
   int kb, ke;
   gemm_krange(p.kmode, p.K, m0, n0, BM, BN, BK, kb, ke);
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(cons
 
   // ---- workspace split-K: combine the k-slices of this tile ----
   if (!(EF & EF_ATOMIC) && p.splitk > 1) {
-    const size_t tile_id = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
+    const size_t tile_id = (size_t)blockIdx.z * p.ntiles + tile_x;
     constexpr int TILE = BM * BN;
     double* mine = p.ws + (tile_id * p.splitk + blockIdx.y) * TILE;
 #pragma unroll
@@ -504,6 +509,22 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(cons
         const int c = n0 + wn * TN * 8 + j * 8 + 2 * t + e;
         if (g == 0 && c < p.N) atomicAdd(p.colsum + c, s);
       }
+  }
+}
+
+template <class Cfg, int LA, int LB, unsigned EF>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_kernel(const GemmParams pin) {
+  extern __shared__ __align__(16) double smem[];
+  gemm_tile_body<Cfg, LA, LB, EF>(pin, blockIdx.x, smem);
+}
+
+// Persistent variant: gridDim.x <= ntiles CTAs, each walking the tile list (same tile order).
+template <class Cfg, int LA, int LB, unsigned EF>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_dmma_persistent_kernel(const GemmParams pin) {
+  extern __shared__ __align__(16) double smem[];
+  for (int tile = blockIdx.x; tile < pin.ntiles; tile += gridDim.x) {
+    gemm_tile_body<Cfg, LA, LB, EF>(pin, tile, smem);
+    __syncthreads();   // every warp is done with the operand stages before the next tile's prologue
   }
 }
 

@@ -47,36 +47,35 @@ __global__ void __launch_bounds__(pcfg::NB + pcfg::RB) panel_kernel(double* __re
   const int row_base = i0 + b + blockIdx.x * RB;
   const int nrows = max(0, min(RB, n - row_base));
 
-  // L2-only (ld.global.cg) loads, 8 in flight per thread: the look-ahead runs this kernel
-  // concurrently with the side-stream trailing update, so L1 must not be trusted.
-  for (int base = 0; base < NB * NB; base += 8 * nthr) {
-    double v[8];
+  // L2-only (ld.global.cg) loads: the look-ahead runs this kernel concurrently with the
+  // side-stream trailing update, so L1 must not be trusted.  All 32 loads a thread owes to each
+  // of the two blocks are issued back to back (one exposed L2 round trip per block, not four).
+  {
+    constexpr int PER = NB * NB / (NB + RB);   // 32 elements per thread per block
+    double v[PER];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * nthr + tid;
+    for (int u = 0; u < PER; ++u) {
+      const int idx = u * nthr + tid;
       const int r = idx >> 6, c = idx & 63;
       v[u] = (r == c) ? 1.0 : 0.0;
-      if (idx < NB * NB && r < b && c < b) v[u] = __ldcg(A + (size_t)(i0 + r) * lda + i0 + c);
+      if (r < b && c < b) v[u] = __ldcg(A + (size_t)(i0 + r) * lda + i0 + c);
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * nthr + tid;
-      if (idx < NB * NB) Rs[(idx >> 6) * LDR + (idx & 63)] = v[u];
+    for (int u = 0; u < PER; ++u) {
+      const int idx = u * nthr + tid;
+      Rs[(idx >> 6) * LDR + (idx & 63)] = v[u];
     }
-  }
-  for (int base = 0; base < RB * NB; base += 8 * nthr) {
-    double v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * nthr + tid;
+    for (int u = 0; u < PER; ++u) {
+      const int idx = u * nthr + tid;
       const int r = idx >> 6, c = idx & 63;
       v[u] = 0.0;
-      if (idx < RB * NB && r < nrows && c < b) v[u] = __ldcg(A + (size_t)(row_base + r) * lda + i0 + c);
+      if (r < nrows && c < b) v[u] = __ldcg(A + (size_t)(row_base + r) * lda + i0 + c);
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * nthr + tid;
-      if (idx < RB * NB) Rs[(NB + (idx >> 6)) * LDR + (idx & 63)] = v[u];
+    for (int u = 0; u < PER; ++u) {
+      const int idx = u * nthr + tid;
+      Rs[(NB + (idx >> 6)) * LDR + (idx & 63)] = v[u];
     }
   }
   __syncthreads();
@@ -427,8 +426,22 @@ int potrf_f64(double* A, int n, int lda, int* info, cudaStream_t st) {
     side_pending = false;
     if (t1 < n) {  // (b) the rest, lower triangle, on the side stream
       double* P1 = A + (size_t)t1 * lda + o;
-      rc = gemm_simple(LK, LK, n - t1, n - t1, w, -1.0, P1, lda, P1, lda, 1.0,
-                       A + (size_t)t1 * lda + t1, lda, true, 0, 1, la->side);
+      // (b) runs beside the next panel's kernel chain.  A full grid would own every SM for one
+      // CTA lifetime (~40 us at K = 256; the 128x128 tile's 65 K registers exclude co-residency)
+      // and the chain's next launch would sit waiting for that long, so the grid is capped (the
+      // persistent GEMM variant walks the tile list) and ~40 SMs stay free for the chain.
+      static const int cap_env = getenv("GPINV_POTRF_B_CAP") ? atoi(getenv("GPINV_POTRF_B_CAP")) : -1;
+      const int T = cdiv(n - t1, 128);
+      const int tiles = T * (T + 1) / 2;
+      (void)tiles;
+      int cap = 108;   // measured optimum at n = 4096 (2.68 ms vs 3.01 ms uncapped; 80: 2.85, 132: 2.81)
+      if (cap_env >= 0) cap = cap_env;
+      GemmParams gp = {};
+      gp.A = P1; gp.lda = lda; gp.B = P1; gp.ldb = lda; gp.M = n - t1; gp.N = n - t1; gp.K = w;
+      gp.alpha = -1.0; gp.beta = 1.0; gp.Cin = A + (size_t)t1 * lda + t1; gp.ldcin = lda;
+      gp.out = A + (size_t)t1 * lda + t1; gp.ldo = lda; gp.splitk = 1; gp.max_ctas = cap;
+      gp.force_cfg = cap > 0 ? 1 : 0;
+      rc = gemm_launch(LK, LK, EF_BETA | EF_LOWER, gp, la->side);
       if (rc) return rc;
       if (cudaEventRecord(la->evB, la->side) != cudaSuccess) return GPINV_ERR_CUDA;
       side_pending = true;
