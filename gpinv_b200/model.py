@@ -47,6 +47,14 @@ class Model(Parameterized):
     def _prepare(self):
         """Hook called before every evaluation (StVGP re-creates q_mu/q_sqrt when X changed)."""
 
+    def _compile(self, optimizer=None, **kw):
+        """GPflow ``Model._compile`` built the TF graph and session here (reference usage:
+        testing/test_stvgp.py:17).  There is no graph to build: the shape re-check of
+        GPinv/stvgp.py:76-94 runs, the library is loaded, the split-K workspace registered."""
+        from . import ops
+        self._prepare()
+        ops.ensure_workspace(default_device())
+
     # ---- objective -------------------------------------------------------------------
     def enable_cuda_graph(self, flag=True):
         """Capture one whole evaluation (forward + hand-written backward, ~100-250 kernel launches)
@@ -426,7 +434,7 @@ class Model(Parameterized):
 
     def _optimize_np(self, method, tol, callback, maxiter, **kw):
         from scipy.optimize import minimize
-        options = dict(disp=False, maxiter=maxiter)
+        options = dict(maxiter=maxiter)
         if "max_iters" in kw:
             options["maxiter"] = kw.pop("max_iters")
         options.update(kw)
@@ -487,9 +495,15 @@ class Model(Parameterized):
         self._prepare()
         if RNG is None:
             RNG = np.random.RandomState(0)
-        return hmc.sample_HMC(self._objective, num_samples, Lmax=Lmax, epsilon=epsilon, thin=thin,
-                              burn=burn, x0=self.get_free_state(), verbose=verbose,
-                              return_logprobs=return_logprobs, RNG=RNG)
+        # device-resident chain: state, momentum and gradient never leave HBM between leapfrog steps
+        out = hmc.sample_HMC_device(self._objective_device, num_samples, Lmax=Lmax, epsilon=epsilon,
+                                    thin=thin, burn=burn, x0=self.get_free_state(),
+                                    device=default_device(), verbose=verbose,
+                                    return_logprobs=return_logprobs, RNG=RNG)
+        # a proposal that left the positive-definite region shows up as NaN and was rejected by
+        # the sampler (GPflow: "numerical instability"): it is not an error of the call
+        self._pending_infos = []
+        return out
 
 
 class GPModel(Model):

@@ -123,6 +123,33 @@ def test_hmc_samples_a_standard_normal():
     assert np.all(np.abs(s.mean(0)) < 0.3) and np.all(np.abs(s.var(0) - 1.0) < 0.4)
 
 
+def test_device_hmc_walks_the_same_chain_as_the_host_loop():
+    """sample_HMC_device (tensors, one host read per iteration) against sample_HMC (numpy) on a
+    correlated Gaussian, incl. thinning and burn-in: same RNG stream, same accept decisions."""
+    import torch
+    from gpinv_b200 import hmc
+    A = np.array([[2.0, 0.3, 0.0], [0.3, 1.0, 0.2], [0.0, 0.2, 0.5]])
+
+    def f_np(x):
+        return 0.5 * x @ A @ x, A @ x
+
+    At = torch.as_tensor(A)
+
+    def f_t(x):
+        return (0.5 * x @ At @ x).reshape(1), At @ x
+
+    x0 = np.array([0.3, -0.2, 0.1])
+    a = hmc.sample_HMC(f_np, 40, Lmax=8, epsilon=0.3, x0=x0, thin=2, burn=5, RNG=np.random.RandomState(4))
+    b = hmc.sample_HMC_device(f_t, 40, Lmax=8, epsilon=0.3, x0=x0, device="cpu", thin=2, burn=5,
+                              RNG=np.random.RandomState(4))
+    assert np.allclose(a, b, rtol=0, atol=1e-12)
+
+    def f_nan(x):                         # NaN gradient: premature reject, the state must not move
+        return torch.zeros(1, dtype=torch.float64), torch.full_like(x, float("nan"))
+    c = hmc.sample_HMC_device(f_nan, 5, Lmax=4, epsilon=0.1, x0=x0, device="cpu", RNG=np.random.RandomState(0))
+    assert np.allclose(c, np.tile(x0, (5, 1)))
+
+
 def test_hmc_rejects_nan_gradient():
     calls = {"n": 0}
 
