@@ -205,7 +205,10 @@ def main():
         gdist.attach(m)
         # torchrun exports OMP_NUM_THREADS=1; the host API stages 134 MB per call with torch's
         # threaded CPU copy, so give every rank its share of the host cores back
-        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
+        # (measured at 2 ranks: 2-4 staging threads per rank beat 8 -- the ranks share the cores
+        # with each other's launch threads)
+        torch.set_num_threads(int(os.environ.get("GPINV_HOST_THREADS",
+                                                 max(2, min(4, (os.cpu_count() or 1) // world)))))
     elif not args.no_graph:
         m.enable_cuda_graph()       # one captured graph per evaluation (~250 launches), replayed
     x_host = m.get_free_state()
@@ -329,7 +332,7 @@ def main():
             "e2e": {"value": 1.0 / t_e2e, "unit": "evals/s",
                     "h2d_bytes_per_step": getattr(m, "_last_h2d_bytes", nbytes),
                     "h2d_note": "x is %d bytes; only the lower trapezoids of q_sqrt (the part tril() reads) are transferred" % nbytes,
-                    "d2h_bytes_per_step": nbytes + 8},
+                    "d2h_bytes_per_step": getattr(m, "_last_d2h_bytes", nbytes + 8)},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": roof,

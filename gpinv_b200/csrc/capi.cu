@@ -59,6 +59,20 @@ int gpinv_set_workspace(void* ptr, size_t bytes) {
 }
 const char* gpinv_last_error(void) { return g_last_error.c_str(); }
 
+int gpinv_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch,
+                         size_t width_bytes, size_t height, int kind, void* stream) {
+  if (width_bytes == 0 || height == 0) return GPINV_OK;
+  if (!dst || !src || dpitch < width_bytes || spitch < width_bytes || kind < 1 || kind > 3) return GPINV_ERR_ARG;
+  const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice
+                         : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  const cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height, k, ST(stream));
+  if (e != cudaSuccess) {
+    set_last_error(cudaGetErrorString(e));
+    return GPINV_ERR_CUDA;
+  }
+  return GPINV_OK;
+}
+
 size_t gpinv_kbuild_ws_bytes(int n, int n2, int D) { return kbuild_ws_bytes(n, n2, D); }
 
 int gpinv_kbuild_f64(const double* X, const double* X2, int n, int n2, int D, int ldx, int ldx2,

@@ -175,6 +175,8 @@ class Model(Parameterized):
             # the upload must be able to slot in between the Cholesky and the sampling stage)
             return self._objective_host_overlapped(x, hin, hout, finish, dev, **kw)
         # torch's CPU copy is multi-threaded; a plain numpy assignment of 134 MB is not
+        hout._gpinv_fresh_zero = False
+        hout._gpinv_upper_zero = None
         hin.copy_(torch.from_numpy(x))
         xd = hin.to(dev, non_blocking=True)
         f, g = self._objective_device(xd, **kw)
@@ -211,7 +213,8 @@ class Model(Parameterized):
             # page-locking 134 MB takes ~100 ms: allocate two at once the first time, because an
             # optimiser typically still holds the previous gradient while it asks for the next
             for _ in range(2 if not pool else 1):
-                ent = [torch.empty(n + 1, dtype=torch.float64).pin_memory(), None]
+                ent = [torch.zeros(n + 1, dtype=torch.float64).pin_memory(), None]
+                ent[0]._gpinv_fresh_zero = True
                 pool.append(ent)
         hout = ent[0]
 
@@ -255,7 +258,7 @@ class Model(Parameterized):
         nq = params[big]._tril_rows
         tri = nq is not None and nq * nq == b1 - b0 and nq >= 512
         ready = threading.Event()
-        state = {"h2d": 0}
+        state = {"h2d": 0, "d2h": 0}
 
         if tri:
             # Only tril(q_sqrt) is read by the model: stage, transfer and scatter the lower
@@ -267,18 +270,37 @@ class Model(Parameterized):
             dstage = torch.empty(total, dtype=torch.float64, device=dev)
             src2, dst2 = xt[b0:b1].view(nq, nq), xbig.view(nq, nq)
 
+            G = 1 if self.dist is None else self.dist.world_size
+            rank = 0 if self.dist is None else self.dist.rank
+            blocks, o = [], 0
+            for r0 in range(0, nq, rb):
+                r1 = min(nq, r0 + rb)
+                blocks.append((r0, r1, o))
+                o += (r1 - r0) * r1
+            if G > 1:
+                # Sample sharding: x is the same on every rank, so the ranks split the staging
+                # work (block k goes to rank k mod G, biggest blocks dealt first) and ONE
+                # all-reduce over NVLink of the zero-initialised packed buffer completes it on
+                # every GPU: per-rank host traffic and PCIe bytes drop by G.
+                dstage.zero_()
+                order = sorted(range(len(blocks)), key=lambda k: -blocks[k][2])
+                mine = set(k for j, k in enumerate(order) if j % G == rank)
+            else:
+                mine = set(range(len(blocks)))
+
             def upload_chunks():
-                o = 0
-                for r0 in range(0, nq, rb):
-                    r1 = min(nq, r0 + rb)
+                for k, (r0, r1, o) in enumerate(blocks):
+                    if k not in mine:
+                        continue
                     cnt = (r1 - r0) * r1
                     st = hin[b0 + o:b0 + o + cnt].view(r1 - r0, r1)
                     st.copy_(src2[r0:r1, :r1])                      # threaded strided host copy
-                    dv = dstage[o:o + cnt].view(r1 - r0, r1)
-                    dv.copy_(st, non_blocking=True)                 # contiguous DMA
-                    dst2[r0:r1, :r1].copy_(dv)                      # strided scatter on the device
-                    o += cnt
+                    dstage[o:o + cnt].view(r1 - r0, r1).copy_(st, non_blocking=True)   # contiguous DMA
                     state["h2d"] += 8 * cnt
+                if G > 1:
+                    self.dist.all_reduce(dstage)
+                for r0, r1, o in blocks:                            # strided scatter on the device
+                    dst2[r0:r1, :r1].copy_(dstage[o:o + (r1 - r0) * r1].view(r1 - r0, r1))
         else:
             xbig = torch.empty(b1 - b0, dtype=torch.float64, device=dev)
 
@@ -340,9 +362,25 @@ class Model(Parameterized):
             keep["g"] = gf
             with torch.cuda.stream(cs):
                 cs.wait_event(ev)
-                hout[1 + b0:1 + b1].copy_(gf, non_blocking=True)
+                if tri and getattr(hout, "_gpinv_upper_zero", None) == (b0, nq):
+                    # the strict upper triangle of this gradient is exactly zero and the pinned
+                    # buffer's upper part has never been written: move the lower trapezoids only
+                    from . import _capi
+                    for r0, r1, _ in blocks:
+                        off = 8 * (r0 * nq)
+                        _capi.check(_capi.lib().gpinv_memcpy2d_async(
+                            hout.data_ptr() + 8 * (1 + b0) + off, 8 * nq, gf.data_ptr() + off, 8 * nq,
+                            8 * r1, r1 - r0, 2, cs.cuda_stream), "memcpy2d")
+                        state["d2h"] += 8 * r1 * (r1 - r0)
+                else:
+                    hout._gpinv_upper_zero = None
+                    hout[1 + b0:1 + b1].copy_(gf, non_blocking=True)
+                    state["d2h"] += 8 * (b1 - b0)
             keep["done"] = True
 
+        if tri and getattr(hout, "_gpinv_fresh_zero", False):
+            hout._gpinv_upper_zero = (b0, nq)       # zero-filled pinned buffer, first use
+        hout._gpinv_fresh_zero = False
         leaves = self.make_tensors(xd, override={big: xbig})
         params[big]._before_use = wait_big
         leaves[big].register_hook(big_grad_hook)
@@ -361,6 +399,8 @@ class Model(Parameterized):
             self.clear_tensors()
             th.join()
         rest = [(i, a, b) for i, (a, b) in enumerate(offs) if not (i == big and keep.get("done"))]
+        if not keep.get("done"):
+            hout._gpinv_upper_zero = None
         parts = [nf.detach().reshape(1)]
         for i, a, b in rest:
             parts.append(torch.zeros(b - a, dtype=torch.float64, device=dev) if grads[i] is None
@@ -380,6 +420,7 @@ class Model(Parameterized):
         self._check_infos()
         out = finish()
         self._last_h2d_bytes = state["h2d"]
+        self._last_d2h_bytes = state["d2h"] + 8 * (1 + n - (b1 - b0))
         tr("done")
         if trace is not None:
             print("e2e-trace " + " ".join("%s=%.2f" % (k, 1e3 * (v - trace[0][1])) for k, v in trace),

@@ -36,6 +36,14 @@ const char* gpinv_last_error(void);
  * Without it the GEMMs run data-parallel only.  Calls that use it must be stream-ordered. */
 int gpinv_set_workspace(void* ptr, size_t bytes);
 
+/* Strided 2-D copy on `stream` (cudaMemcpy2DAsync): `height` rows of `width_bytes`, row pitches in
+ * bytes; kind 1 = host->device, 2 = device->host, 3 = device->device.  Used by the host API of
+ * Model._objective (the boundary the reference's GPflow Model._objective closure forms,
+ * pattern at GPinv/model.py:64-75) to move only the lower trapezoids of the q_sqrt gradient into
+ * pinned host memory. */
+int gpinv_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch,
+                         size_t width_bytes, size_t height, int kind, void* stream);
+
 /* --- T1-T3: kernel core matrix.  Replaces Kern._Kcore + jitter (GPinv/kernels.py:57-58,
  * 105-107,115-120,140-145; GPflow Stationary.square_dist).  X [n,D], X2 [n2,D] or NULL
  * (then K is n x n and `jitter` is added to its diagonal); ls device [D] (ard) or [1]. */
