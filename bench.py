@@ -205,10 +205,11 @@ def main():
         gdist.attach(m)
         # torchrun exports OMP_NUM_THREADS=1; the host API stages 134 MB per call with torch's
         # threaded CPU copy, so give every rank its share of the host cores back
-        # (measured at 2 ranks: 2-4 staging threads per rank beat 8 -- the ranks share the cores
-        # with each other's launch threads)
+        # -- half a core share per rank, at most 4: every rank also runs a launch thread, an
+        # autograd thread and NCCL's proxy (measured on the 16-core box: 8 ranks x 2 staging
+        # threads -> stragglers, 42 evals/s end to end; 8 x 1 -> 78; 2 ranks: 2-4 threads beat 8)
         torch.set_num_threads(int(os.environ.get("GPINV_HOST_THREADS",
-                                                 max(2, min(4, (os.cpu_count() or 1) // world)))))
+                                                 max(1, min(4, (os.cpu_count() or 1) // (2 * world))))))
     elif not args.no_graph:
         m.enable_cuda_graph()       # one captured graph per evaluation (~250 launches), replayed
     x_host = m.get_free_state()
