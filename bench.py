@@ -210,8 +210,10 @@ def main():
         # threads -> stragglers, 42 evals/s end to end; 8 x 1 -> 78; 2 ranks: 2-4 threads beat 8)
         torch.set_num_threads(int(os.environ.get("GPINV_HOST_THREADS",
                                                  max(1, min(4, (os.cpu_count() or 1) // (2 * world))))))
-    elif not args.no_graph:
-        m.enable_cuda_graph()       # one captured graph per evaluation (~250 launches), replayed
+    if not args.no_graph:
+        # one captured graph per evaluation (~250 launches), replayed; with sample sharding the
+        # graph holds the rank-local part and the NCCL all-reduce follows it eagerly
+        m.enable_cuda_graph()
     x_host = m.get_free_state()
     x = torch.as_tensor(x_host).to(dev)
     eps = torch.randn((1, S, n), dtype=torch.float64, device=dev,

@@ -70,9 +70,7 @@ class Model(Parameterized):
 
     def _objective_device(self, x: torch.Tensor, **kw):
         """(-f, -df/dx) as CUDA tensors ([1] and [|x|]); no host synchronisation."""
-        if self._use_graph and self.dist is None:
-            # (sample-sharded evaluations stay eager: a captured NCCL all-reduce gained < 0.5 ms
-            # at 2 GPUs and made process-group teardown hang)
+        if self._use_graph:
             return self._objective_graphed(x, **kw)
         return self._objective_eager(x, **kw)
 
@@ -87,14 +85,17 @@ class Model(Parameterized):
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
             side.wait_stream(cur)
+            # Under sample sharding the graph holds this rank's LOCAL evaluation only; the all-reduce
+            # of its static output runs eagerly after every replay (a captured NCCL collective
+            # gained nothing measurable and made process-group teardown hang).
             with torch.cuda.stream(side):
                 for _ in range(3):      # warm-up: lazy attribute setting, workspace registration
-                    self._objective_eager(sx, **sdyn)
+                    self._objective_eager(sx, reduce=False, **sdyn)
             cur.wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                f, g = self._objective_eager(sx, **sdyn)
+                f, g = self._objective_eager(sx, reduce=False, **sdyn)
             ent = (graph, sx, sdyn, f, g, list(self._pending_infos))
             self._graphs[key] = ent
         graph, sx, sdyn, f, g, infos = ent
@@ -103,14 +104,18 @@ class Model(Parameterized):
             sdyn[k].copy_(v)
         graph.replay()
         self._pending_infos = list(infos)
+        if self.dist is not None:
+            self.dist.all_reduce(f._base if f._base is not None else torch.cat([f, g]))
         return f, g
 
-    def _objective_eager(self, x: torch.Tensor, **kw):
+    def _objective_eager(self, x: torch.Tensor, reduce=True, **kw):
+        """One evaluation, launched kernel by kernel.  ``reduce=False`` (graph capture under
+        sample sharding) returns this rank's partial [-f, -grad] without the all-reduce."""
         self._prepare()
         leaves = self.make_tensors(x)
         self._pending_infos = []
         early = {}
-        if self.dist is not None and self.dist.world_size > 1 and leaves:
+        if reduce and self.dist is not None and self.dist.world_size > 1 and leaves:
             # Sample sharding: the gradient of the largest block (q_sqrt, 134 MB at the headline
             # size) exists as soon as the sampling stage's reverse pass is done; its all-reduce
             # starts there, on NCCL's stream, and overlaps the Cholesky reverse sweep.
@@ -145,7 +150,7 @@ class Model(Parameterized):
             buf = torch.cat([small[:n0], early["grad"].reshape(-1), small[n0:]])
             return buf[:1], buf[1:]
         buf = torch.cat([nf.detach().reshape(1)] + parts)
-        if self.dist is not None:
+        if reduce and self.dist is not None:
             self.dist.all_reduce(buf)
         return buf[:1], buf[1:]
 

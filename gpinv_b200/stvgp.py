@@ -69,19 +69,27 @@ class StVGP(GPModel):
         return torch.randn((self.num_latent, S, self.num_data), dtype=torch.float64, device=dev,
                            generator=self._generator)
 
-    def _eps_tensor(self, eps, S):
+    def _eps_full(self, eps, S):
+        """All S draws [R,S,n] on the device (drawn here when not given)."""
         if eps is None:
             eps = self._draw_eps(S)
         elif not isinstance(eps, torch.Tensor):
             eps = torch.as_tensor(np.ascontiguousarray(eps, dtype=np.float64)).to(default_device())
+        return eps
+
+    def _eps_tensor(self, eps, S):
+        """This rank's share of the draws (all of them without sample sharding)."""
+        eps = self._eps_full(eps, S)
         if self.dist is not None:
             eps = self.dist.shard_samples(eps)
         return eps.contiguous()
 
     def _graph_inputs(self, kw):
+        # the graph's static input holds ALL draws: build_likelihood takes its shard inside the
+        # capture and divides by the global S
         eps = kw.get("eps")
         S = self.num_samples if eps is None else eps.shape[1]
-        return {"eps": self._eps_tensor(eps, S)}
+        return {"eps": self._eps_full(eps, S).contiguous()}
 
     def build_likelihood(self, eps=None):
         """Variational lower bound with stochastic approximation (GPinv/stvgp.py:96-107)."""

@@ -448,11 +448,14 @@ for overlap_min in (1 << 30, 1000):                               # plain host p
         if not good:
             print("rank %d overlap_min %d: f %r vs %r, grad rel err %.3e" % (rank, overlap_min, f1, f0, rel_err(g1, g0)), flush=True)
         ok = ok and good
-fd, gd = m._objective_device(torch.as_tensor(x).cuda(), eps=torch.as_tensor(eps).cuda())
-good = close(float(fd), gd.cpu().numpy())
-if not good:
-    print("rank %d device path: f %r vs %r, grad rel err %.3e" % (rank, float(fd), f0, rel_err(gd.cpu().numpy(), g0)), flush=True)
-ok = ok and good
+for graph in (False, True):                                       # eager, then graph replay + eager all-reduce
+    m.enable_cuda_graph(graph)
+    for _ in range(2):
+        fd, gd = m._objective_device(torch.as_tensor(x).cuda(), eps=torch.as_tensor(eps).cuda())
+        good = close(float(fd), gd.cpu().numpy())
+        if not good:
+            print("rank %d device path graph=%s: f %r vs %r, grad rel err %.3e" % (rank, graph, float(fd), f0, rel_err(gd.cpu().numpy(), g0)), flush=True)
+        ok = ok and good
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 3)
