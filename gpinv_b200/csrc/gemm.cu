@@ -187,9 +187,9 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
       p.splitk = cached;
       p.ws_cnt = static_cast<int*>(w->ptr);
       p.ws = reinterpret_cast<double*>(static_cast<char*>(w->ptr) + CNT_SLOTS * sizeof(int));
-    } else if (w && cached < 0 && T <= CNT_SLOTS && T1 <= 4096) {
+    } else if (w && cached < 0 && T <= CNT_SLOTS / 2 && T1 <= 4096) {
       const size_t tile_bytes = 128 * 128 * sizeof(double);
-      const size_t cap = (w->bytes > CNT_SLOTS * sizeof(int)) ? (w->bytes - CNT_SLOTS * sizeof(int)) / tile_bytes : 0;
+      const size_t cap = (w->bytes > CNT_SLOTS * sizeof(int)) ? (w->bytes - CNT_SLOTS * sizeof(int)) / tile_bytes / 2 : 0;
       static thread_local int kt[4096];
       for (int i = 0; i < T1; ++i) {
         int tm, tn, kb, ke;
@@ -237,10 +237,6 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
       }
     }
   }
-  static const bool log_gemm = (getenv("GPINV_GEMM_LOG") != nullptr);
-  if (log_gemm)
-    fprintf(stderr, "gemm-log la=%d lb=%d ef=%u M=%d N=%d K=%d kmode=%d splitk=%d batch=%d cfg=%s\n", la, lb, ef,
-            p.M, p.N, p.K, p.kmode, p.splitk, p.batch, small ? "small" : "big");
   // ---- k-split for the 64x64 configuration: a few hundred short tiles cannot fill 148 SMs x 3
   // resident CTAs (e.g. the 1024^3 triangular products of the Cholesky reverse leaves: 136 tiles)
   if (p.allow_split && !no_split && p.splitk == 1 && !(ef & EF_ATOMIC) && small) {
@@ -253,13 +249,22 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
     s_ = min(s_, ktiles / 12);          // >= 12 k-tiles (192 columns of K) per slice
     s_ = min(s_, 4);
     const size_t tile_bytes = 64 * 64 * sizeof(double);
-    const size_t cap = (w && w->bytes > CNT_SLOTS * sizeof(int)) ? (w->bytes - CNT_SLOTS * sizeof(int)) / tile_bytes : 0;
-    if (w && s_ >= 2 && T <= CNT_SLOTS && (size_t)(T * s_) <= cap) {
+    const size_t cap = (w && w->bytes > CNT_SLOTS * sizeof(int)) ? (w->bytes - CNT_SLOTS * sizeof(int)) / tile_bytes / 2 : 0;
+    if (w && s_ >= 2 && T <= CNT_SLOTS / 2 && (size_t)(T * s_) <= cap) {
       p.splitk = s_;
       p.ws_cnt = static_cast<int*>(w->ptr);
       p.ws = reinterpret_cast<double*>(static_cast<char*>(w->ptr) + CNT_SLOTS * sizeof(int));
     }
   }
+  if (p.splitk > 1 && p.ws && p.ws_slot == 1) {   // second half of the workspace
+    WsReg* w = ws_for_device();
+    p.ws_cnt += CNT_SLOTS / 2;
+    p.ws += ((w->bytes - CNT_SLOTS * sizeof(int)) / sizeof(double)) / 2;
+  }
+  static const bool log_gemm = (getenv("GPINV_GEMM_LOG") != nullptr);
+  if (log_gemm)
+    fprintf(stderr, "gemm-log la=%d lb=%d ef=%u M=%d N=%d K=%d kmode=%d splitk=%d batch=%d cfg=%s\n", la, lb, ef,
+            p.M, p.N, p.K, p.kmode, p.splitk, p.batch, small ? "small" : "big");
   if (small) return dispatch<CfgSmall>(la, lb, ef, p, stream);
   static const int big_bk = getenv("GPINV_BIG_BK") ? atoi(getenv("GPINV_BIG_BK")) : 16;
   if (big_bk == 32 || p.force_cfg == 3) return dispatch<CfgBig32>(la, lb, ef, p, stream);

@@ -76,6 +76,9 @@ struct GemmParams {
   // first sampling product): they must leave SMs free instead of flooding the machine.
   int max_ctas;
   int ntiles;   // filled by the launcher
+  // The registered split-K workspace is used in two halves so that two k-split GEMMs may run
+  // concurrently on two streams (Cholesky reverse sweep): ws_slot 0 / 1 selects the half.
+  int ws_slot;
 };
 
 template <int TM_, int TN_, int WM_, int WN_, int STAGES_, int MINB_, int BK_ = 16>

@@ -772,8 +772,9 @@ int potrf_bwd_inv_f64(const double* L, int ldl, double* Ab, int ldab, int n, dou
 // ---------------------------------------------------------------------------------------
 static int gemm_ws(int la, int lb, unsigned ef, int M, int N, int K, double alpha, const double* A,
                    int lda, const double* B, int ldb, double beta, const double* Cin, int ldcin,
-                   double* out, int ldo, int kmode, cudaStream_t st) {
+                   double* out, int ldo, int kmode, cudaStream_t st, int ws_slot = 0) {
   GemmParams p = {};
+  p.ws_slot = ws_slot;
   p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.M = M; p.N = N; p.K = K;
   p.alpha = alpha; p.beta = beta; p.Cin = Cin; p.ldcin = ldcin; p.out = out; p.ldo = ldo;
   p.kmode = kmode; p.splitk = 1; p.allow_split = 1;
@@ -804,6 +805,9 @@ int potrf_bwd_hybrid_f64(const double* L, int ldl, double* Ab, int ldab, int n, 
   zero_upper_kernel<<<grd, blk, 0, st>>>(Ab, n, ldab);
   GPINV_CHECK_LAUNCH();
   const int nblocks = cdiv(n, m);
+  static const bool no_fork = (getenv("GPINV_BWD_NO_FORK") != nullptr);
+  LookAhead* la2 = no_fork ? nullptr : lookahead_for_current_device();
+  bool forked = false;
   for (int b = nblocks - 1; b >= 0; --b) {
     const int s = b * m, e = min(n, s + m), bw = e - s, r = n - e;
     const double* Wbb = W + (size_t)s * n + s;
@@ -817,10 +821,28 @@ int potrf_bwd_hybrid_f64(const double* L, int ldl, double* Ab, int ldab, int n, 
       if (cudaMemcpy2DAsync(Cb, (size_t)ldab * sizeof(double), S1, (size_t)bw * sizeof(double),
                             (size_t)bw * sizeof(double), r, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         return GPINV_ERR_CUDA;
-      if (s > 0) {  // Bbar -= Cbar R
+      // Two independent chains follow from Cbar: {Bbar -= Cbar R, Rbar -= Cbar^T B} (big GEMMs) and
+      // {Dbar -= tril(Cbar^T C), diagonal-block reverse} (small, latency-bound GEMMs).  The first
+      // runs on the side stream (second half of the split-K workspace) beside the second.
+      forked = false;
+      if (s > 0 && la2) {
+        if (cudaEventRecord(la2->evP, st) != cudaSuccess) return GPINV_ERR_CUDA;
+        if (cudaStreamWaitEvent(la2->side, la2->evP, 0) != cudaSuccess) return GPINV_ERR_CUDA;
+        forked = true;
+      }
+      if (s > 0) {
+        cudaStream_t s2 = forked ? la2->side : st;
+        const int slot = forked ? 1 : 0;
+        // Bbar -= Cbar R
         rc = gemm_ws(LK, LMN, EF_BETA, r, s, bw, -1.0, Cb, ldab, L + (size_t)s * ldl, ldl, 1.0,
-                     Ab + (size_t)e * ldab, ldab, Ab + (size_t)e * ldab, ldab, 0, st);
+                     Ab + (size_t)e * ldab, ldab, Ab + (size_t)e * ldab, ldab, 0, s2, slot);
         if (rc) return rc;
+        // Rbar -= Cbar^T B
+        double* Rb2 = Ab + (size_t)s * ldab;
+        rc = gemm_ws(LMN, LMN, EF_BETA, bw, s, r, -1.0, Cb, ldab, L + (size_t)e * ldl, ldl, 1.0, Rb2, ldab,
+                     Rb2, ldab, 0, s2, slot);
+        if (rc) return rc;
+        if (forked && cudaEventRecord(la2->evB, la2->side) != cudaSuccess) return GPINV_ERR_CUDA;
       }
       // Dbar -= tril(Cbar^T C)
       rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, r, -1.0, Cb, ldab, L + (size_t)e * ldl + s, ldl,
@@ -850,11 +872,8 @@ int potrf_bwd_hybrid_f64(const double* L, int ldl, double* Ab, int ldab, int n, 
     }
     if (s > 0) {
       double* Rb = Ab + (size_t)s * ldab;               // Rbar: block rows, columns [0, s)
-      if (r > 0) {  // Rbar -= Cbar^T B
-        rc = gemm_ws(LMN, LMN, EF_BETA, bw, s, r, -1.0, Cb, ldab, L + (size_t)e * ldl, ldl, 1.0, Rb, ldab,
-                     Rb, ldab, 0, st);
-        if (rc) return rc;
-      }
+      if (forked && cudaStreamWaitEvent(st, la2->evB, 0) != cudaSuccess) return GPINV_ERR_CUDA;
+      forked = false;
       // Rbar -= (Dbar + Dbar^T) R
       dim3 g2(cdiv(bw, 32), cdiv(bw, 8));
       symmetrize_block_kernel<<<g2, blk, 0, st>>>(Ab, ldab, s, bw, S2);

@@ -75,7 +75,7 @@ def spd(n, seed):
 
 
 def check_potrf():
-    for n in (1, 5, 64, 65, 100, 256, 300, 515, 1024, 1100, 2048, 2500):   # > 1024: hybrid blocked reverse
+    for n in (1, 5, 64, 65, 100, 256, 300, 515, 1024, 1100, 2048, 2500, 3072):   # > 1024: hybrid blocked reverse
         K = spd(n, n)
         Kt = torch.tensor(K, requires_grad=True)
         Lref = torch.linalg.cholesky(Kt)
@@ -88,6 +88,12 @@ def check_potrf():
         (gref,) = torch.autograd.grad((Lref * torch.tensor(Lbar)).sum(), Kt)
         (gout,) = torch.autograd.grad((L * t(Lbar)).sum(), Kd)
         report("potrf_bwd n=%d" % n, rel(gout, gref), 1e-9)
+        if n > 2048:
+            # three blocks: the reverse sweep forks onto a side stream (second half of the split-K
+            # workspace); repeated calls run with warm plans, i.e. with real concurrency
+            for rep in range(2):
+                (g2,) = torch.autograd.grad((ops.potrf(Kd)[0] * t(Lbar)).sum(), Kd)
+                report("potrf_bwd n=%d repeat %d" % (n, rep), rel(g2, gref), 1e-9)
     # ill-conditioned kernel matrices at the headline size (cond ~1e9); repeated to catch races
     for n in (3000, 4096):
         x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)[:, None]
