@@ -34,6 +34,10 @@ SIGNATURES = {
     "gpinv_potrf_f64": (_I, [_P, _I, _I, _P, _P]),
     "gpinv_potrf_bwd_ws_bytes": (_Z, [_I]),
     "gpinv_potrf_bwd_f64": (_I, [_P, _I, _P, _I, _I, _P, _P]),
+    "gpinv_chol_core_ws_bytes": (_Z, [_I, _I]),
+    "gpinv_chol_core_f64": (_I, [_P, _I, _I, _I, _P, _I, _I, _D, _P, _I, _P, _P, _P]),
+    "gpinv_chol_core_bwd_ws_bytes": (_Z, [_I, _I]),
+    "gpinv_chol_core_bwd_f64": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
     "gpinv_trsm_rlt_f64": (_I, [_P, _I, _P, _I, _I, _I, _P]),
     "gpinv_gemm_f64": (_I, [_I, _I, _I, _I, _I, _D, _P, _I, _P, _I, _D, _P, _I, _I, _P]),
     "gpinv_tril_unpack_f64": (_I, [_P, _P, _I, _I, _P]),

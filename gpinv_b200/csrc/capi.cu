@@ -24,6 +24,13 @@ size_t potrf_bwd_inv_ws_bytes(int);
 int potrf_bwd_inv_f64(const double*, int, double*, int, int, double*, cudaStream_t);
 int potrf_bwd_hybrid_f64(const double*, int, double*, int, int, double*, cudaStream_t);
 int potrf_bwd_hybrid_block();
+int potrf_bwd_hybrid_ex_f64(const double*, int, double*, int, int, double*, int, int, cudaStream_t);
+int potrf_ex_f64(double*, int, int, int*, int, cudaStream_t);
+int tril_copy_f64(const double*, int, double*, int, int, cudaStream_t);
+int kbuild_ex_f64(const double*, const double*, int, int, int, int, int, const double*, int, int, double,
+                  double*, int, double*, int, cudaStream_t);
+int kbuild_bwd_ex_f64(const double*, const double*, int, int, int, int, int, const double*, int, int,
+                      const double*, int, double*, double*, int, cudaStream_t);
 int tril_unpack_f64(const double*, double*, int, int, cudaStream_t);
 int tril_pack_f64(const double*, double*, int, int, cudaStream_t);
 int sumsq_f64(const double*, size_t, double*, cudaStream_t);
@@ -117,6 +124,36 @@ int gpinv_potrf_bwd_f64(const double* L, int ldl, double* Abar, int ldab, int n,
   if (mode == 0 && n > potrf_bwd_hybrid_block())
     return potrf_bwd_hybrid_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
   return potrf_bwd_inv_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
+}
+
+// ---- fused kernel build + Cholesky (the Kern.Cholesky core of GPinv/kernels.py:56-59) ----
+size_t gpinv_chol_core_ws_bytes(int n, int D) { return kbuild_ws_bytes(n, n, D); }
+
+int gpinv_chol_core_f64(const double* X, int n, int D, int ldx, const double* ls, int ard, int mode,
+                        double jitter, double* L, int ldl, int* info, void* ws, void* stream) {
+  if (n <= 0 || D <= 0 || ldl < n) return GPINV_ERR_ARG;
+  int rc = kbuild_ex_f64(X, nullptr, n, n, D, ldx, ldx, ls, ard, mode, jitter, L, ldl,
+                         static_cast<double*>(ws), 1, ST(stream));
+  if (rc) return rc;
+  return potrf_ex_f64(L, n, ldl, info, 1, ST(stream));
+}
+
+size_t gpinv_chol_core_bwd_ws_bytes(int n, int D) {
+  return (size_t)4 * n * n * sizeof(double) + kbuild_ws_bytes(n, n, D);
+}
+
+int gpinv_chol_core_bwd_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
+                            int mode, const double* L, int ldl, const double* Lbar, int ldlb,
+                            double* ls_bar, void* ws, void* stream) {
+  if (n <= 0 || D <= 0 || ldl < n || ldlb < n) return GPINV_ERR_ARG;
+  double* Ab = static_cast<double*>(ws);              // n x n: tril(Lbar), then the Murray-lower Kbar
+  double* sweep_ws = Ab + (size_t)n * n;              // 3 n^2
+  double* kws = sweep_ws + (size_t)3 * n * n;
+  int rc = tril_copy_f64(Lbar, ldlb, Ab, n, n, ST(stream));
+  if (rc) return rc;
+  rc = potrf_bwd_hybrid_ex_f64(L, ldl, Ab, n, n, sweep_ws, 1, 0, ST(stream));
+  if (rc) return rc;
+  return kbuild_bwd_ex_f64(X, nullptr, n, n, D, ldx, ldx, ls, ard, mode, Ab, n, ls_bar, kws, 1, ST(stream));
 }
 
 int gpinv_trsm_rlt_f64(const double* L, int ldl, double* X, int ldx, int m, int n, void* stream) {

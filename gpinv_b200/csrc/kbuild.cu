@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const double* __restrict__ 
                                                      const double* __restrict__ xs2,
                                                      const double* __restrict__ sq2, int n, int n2,
                                                      int D, double jitter, int add_jitter,
-                                                     double* __restrict__ K, int ldk, int vec) {
+                                                     double* __restrict__ K, int ldk, int vec,
+                                                     int lower_only) {
   const int c = 2 * (blockIdx.x * 64 + (threadIdx.x & 63));
   const int rb = blockIdx.y * 16 + (threadIdx.x >> 6) * 4;
   if (c >= n2) return;
@@ -54,6 +55,15 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const double* __restrict__ 
   for (int rr = 0; rr < 4; ++rr) {
     const int r = rb + rr;
     if (r >= n) break;
+    if (lower_only && c > r) {   // strictly above the diagonal: exact zeros, no exp
+      double* o = K + (size_t)r * ldk + c;
+      if (two && vec) *reinterpret_cast<double2*>(o) = make_double2(0.0, 0.0);
+      else {
+        o[0] = 0.0;
+        if (two) o[1] = 0.0;
+      }
+      continue;
+    }
     double dot0 = 0.0, dot1 = 0.0;
     for (int d = 0; d < D; ++d) {
       const double xi = xs1[(size_t)r * D + d];
@@ -67,6 +77,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const double* __restrict__ 
       if (r == c) v0 += jitter;
       if (r == c + 1) v1 += jitter;
     }
+    if (lower_only && c + 1 > r) v1 = 0.0;
     double* o = K + (size_t)r * ldk + c;
     if (two && vec) *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
     else {
@@ -86,7 +97,7 @@ __global__ void __launch_bounds__(256) kbuild_bwd_kernel(const double* __restric
                                                          int n2, int D, int dsel,
                                                          const double* __restrict__ ls,
                                                          const double* __restrict__ Kbar, int ldkb,
-                                                         double* __restrict__ ls_bar) {
+                                                         double* __restrict__ ls_bar, int lower_only) {
   __shared__ double red[32];
   double acc = 0.0;
   const int c = 2 * (blockIdx.x * 64 + (threadIdx.x & 63));
@@ -99,6 +110,7 @@ __global__ void __launch_bounds__(256) kbuild_bwd_kernel(const double* __restric
       for (int e = 0; e < 2; ++e) {
         const int cc = c + e;
         if (cc >= n2) break;
+        if (lower_only && cc > r) break;   // Kbar holds a lower triangle (strict part pre-doubled)
         double dot = 0.0, dsel_dot = 0.0, dsel_sq = 0.0;
         for (int d = 0; d < D; ++d) {
           const double xi = xs1[(size_t)r * D + d], xj = xs2[(size_t)cc * D + d];
@@ -135,9 +147,20 @@ static void kprep(const double* X, int n, int D, int ldx, const double* ls, int 
   kprep_kernel<<<cdiv(n, 256), 256, 0, st>>>(X, n, D, ldx, ls, ard, mode, xs, sq);
 }
 
+int kbuild_ex_f64(const double* X, const double* X2, int n, int n2, int D, int ldx, int ldx2,
+                  const double* ls, int ard, int mode, double jitter, double* K, int ldk, double* ws,
+                  int lower_only, cudaStream_t st);
+
 int kbuild_f64(const double* X, const double* X2, int n, int n2, int D, int ldx, int ldx2,
                const double* ls, int ard, int mode, double jitter, double* K, int ldk, double* ws,
                cudaStream_t st) {
+  return kbuild_ex_f64(X, X2, n, n2, D, ldx, ldx2, ls, ard, mode, jitter, K, ldk, ws, 0, st);
+}
+
+// lower_only (X2 == NULL): the strict upper triangle is written as exact zeros and never evaluated
+int kbuild_ex_f64(const double* X, const double* X2, int n, int n2, int D, int ldx, int ldx2,
+                  const double* ls, int ard, int mode, double jitter, double* K, int ldk, double* ws,
+                  int lower_only, cudaStream_t st) {
   if (n <= 0 || D <= 0 || mode < 0 || mode > 2) return GPINV_ERR_ARG;
   double* xs1 = ws;
   double* sq1 = xs1 + (size_t)n * D;
@@ -153,16 +176,29 @@ int kbuild_f64(const double* X, const double* X2, int n, int n2, int D, int ldx,
   const int add_j = (X2 == nullptr) && (jitter != 0.0);
   const int vec = ((reinterpret_cast<uintptr_t>(K) & 15u) == 0) && (ldk % 2 == 0);
   dim3 grid(cdiv(n2, 128), cdiv(n, 16));
-  if (mode == 0) kbuild_kernel<0><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, jitter, add_j, K, ldk, vec);
-  else if (mode == 1) kbuild_kernel<1><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, jitter, add_j, K, ldk, vec);
-  else kbuild_kernel<2><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, jitter, add_j, K, ldk, vec);
+  if (X2) lower_only = 0;
+  if (mode == 0) kbuild_kernel<0><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, jitter, add_j, K, ldk, vec, lower_only);
+  else if (mode == 1) kbuild_kernel<1><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, jitter, add_j, K, ldk, vec, lower_only);
+  else kbuild_kernel<2><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, jitter, add_j, K, ldk, vec, lower_only);
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
 }
 
+int kbuild_bwd_ex_f64(const double* X, const double* X2, int n, int n2, int D, int ldx, int ldx2,
+                      const double* ls, int ard, int mode, const double* Kbar, int ldkb,
+                      double* ls_bar, double* ws, int lower_only, cudaStream_t st);
+
 int kbuild_bwd_f64(const double* X, const double* X2, int n, int n2, int D, int ldx, int ldx2,
                    const double* ls, int ard, int mode, const double* Kbar, int ldkb,
                    double* ls_bar, double* ws, cudaStream_t st) {
+  return kbuild_bwd_ex_f64(X, X2, n, n2, D, ldx, ldx2, ls, ard, mode, Kbar, ldkb, ls_bar, ws, 0, st);
+}
+
+// lower_only (X2 == NULL): Kbar is a lower triangle whose strict part already carries the factor
+// 2 of the symmetric pair (the blocked Cholesky reverse sweep leaves it in that convention)
+int kbuild_bwd_ex_f64(const double* X, const double* X2, int n, int n2, int D, int ldx, int ldx2,
+                      const double* ls, int ard, int mode, const double* Kbar, int ldkb,
+                      double* ls_bar, double* ws, int lower_only, cudaStream_t st) {
   if (n <= 0 || D <= 0 || mode < 0 || mode > 2) return GPINV_ERR_ARG;
   double* xs1 = ws;
   double* sq1 = xs1 + (size_t)n * D;
@@ -180,9 +216,10 @@ int kbuild_bwd_f64(const double* X, const double* X2, int n, int n2, int D, int 
   dim3 grid(cdiv(n2, 128), cdiv(n, 16));
   for (int l = 0; l < nls; ++l) {
     const int dsel = ard ? l : -1;
-    if (mode == 0) kbuild_bwd_kernel<0><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, dsel, ls, Kbar, ldkb, ls_bar);
-    else if (mode == 1) kbuild_bwd_kernel<1><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, dsel, ls, Kbar, ldkb, ls_bar);
-    else kbuild_bwd_kernel<2><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, dsel, ls, Kbar, ldkb, ls_bar);
+    const int lo = X2 ? 0 : lower_only;
+    if (mode == 0) kbuild_bwd_kernel<0><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, dsel, ls, Kbar, ldkb, ls_bar, lo);
+    else if (mode == 1) kbuild_bwd_kernel<1><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, dsel, ls, Kbar, ldkb, ls_bar, lo);
+    else kbuild_bwd_kernel<2><<<grid, 256, 0, st>>>(xs1, sq1, xs2, sq2, n, n2, D, dsel, ls, Kbar, ldkb, ls_bar, lo);
     GPINV_CHECK_LAUNCH();
   }
   return GPINV_OK;

@@ -383,7 +383,24 @@ static LookAhead* lookahead_for_current_device() {
 // trailing update is split into (a) the columns of the NEXT outer panel, done on the caller's
 // stream so panel o+1 can start at once, and (b) the rest of the trailing matrix, done on a side
 // stream concurrently with (a) and with the factorisation of panel o+1.
+// strict upper part of every NBO x NBO diagonal block <- 0
+__global__ void zero_upper_diag_blocks_kernel(double* __restrict__ A, int n, int lda, int nbo) {
+  const int base = blockIdx.z * nbo;
+  const int c = base + blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = base + blockIdx.y * blockDim.y + threadIdx.y;
+  if (r < n && c < n && c < base + nbo && r < base + nbo && c > r) A[(size_t)r * lda + c] = 0.0;
+}
+
+int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaStream_t st);
+
 int potrf_f64(double* A, int n, int lda, int* info, cudaStream_t st) {
+  return potrf_ex_f64(A, n, lda, info, 0, st);
+}
+
+// upper_is_zero: the caller built only the lower triangle (strict upper part = 0).  The
+// factorisation never reads above the diagonal and only dirties the upper parts of the NBO-wide
+// diagonal blocks, so the final clean-up touches those instead of the whole matrix.
+int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaStream_t st) {
   using namespace pcfg;
   int rc = set_smem_attrs();
   if (rc) return rc;
@@ -448,8 +465,14 @@ int potrf_f64(double* A, int n, int lda, int* info, cudaStream_t st) {
     }
   }
   if (side_pending && cudaStreamWaitEvent(st, la->evB, 0) != cudaSuccess) return GPINV_ERR_CUDA;
-  dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n, 8));
-  zero_upper_kernel<<<grd, blk, 0, st>>>(A, n, lda);
+  dim3 blk(32, 8);
+  if (upper_is_zero) {
+    dim3 grd(cdiv(NBO, 32), cdiv(NBO, 8), cdiv(n, NBO));
+    zero_upper_diag_blocks_kernel<<<grd, blk, 0, st>>>(A, n, lda, NBO);
+  } else {
+    dim3 grd(cdiv(n, 32), cdiv(n, 8));
+    zero_upper_kernel<<<grd, blk, 0, st>>>(A, n, lda);
+  }
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
 }
@@ -792,8 +815,18 @@ static int bwd_block() {
   return m;
 }
 
+int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int n, double* ws,
+                            int ab_is_tril, int finalize, cudaStream_t st);
+
 int potrf_bwd_hybrid_f64(const double* L, int ldl, double* Ab, int ldab, int n, double* ws,
                          cudaStream_t st) {
+  return potrf_bwd_hybrid_ex_f64(L, ldl, Ab, ldab, n, ws, 0, 1, st);
+}
+
+// ab_is_tril: Ab already has a zero strict upper part.  finalize = 0 leaves the result as a lower
+// triangle in Murray's convention (strict lower part = 2 x the symmetric gradient entry).
+int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int n, double* ws,
+                            int ab_is_tril, int finalize, cudaStream_t st) {
   const int m = bwd_block();
   double* W = ws;                       // n x n, only the m x m diagonal blocks are non-zero
   double* S1 = W + (size_t)n * n;       // scratch: Cbar W_bb  /  P
@@ -802,8 +835,10 @@ int potrf_bwd_hybrid_f64(const double* L, int ldl, double* Ab, int ldab, int n, 
   int rc = trtri_f64(L, ldl, W, S1, n, st, m);
   if (rc) return rc;
   dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n, 8));
-  zero_upper_kernel<<<grd, blk, 0, st>>>(Ab, n, ldab);
-  GPINV_CHECK_LAUNCH();
+  if (!ab_is_tril) {
+    zero_upper_kernel<<<grd, blk, 0, st>>>(Ab, n, ldab);
+    GPINV_CHECK_LAUNCH();
+  }
   const int nblocks = cdiv(n, m);
   static const bool no_fork = (getenv("GPINV_BWD_NO_FORK") != nullptr);
   LookAhead* la2 = no_fork ? nullptr : lookahead_for_current_device();
@@ -883,7 +918,24 @@ int potrf_bwd_hybrid_f64(const double* L, int ldl, double* Ab, int ldab, int n, 
       if (rc) return rc;
     }
   }
-  finalize_sym_kernel<<<grd, blk, 0, st>>>(Ab, n, ldab);
+  if (finalize) {
+    finalize_sym_kernel<<<grd, blk, 0, st>>>(Ab, n, ldab);
+    GPINV_CHECK_LAUNCH();
+  }
+  return GPINV_OK;
+}
+
+// dst (ld = ldd) <- tril(src)
+__global__ void tril_copy_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst,
+                                 int ldd, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r < n && c < n) dst[(size_t)r * ldd + c] = (c <= r) ? src[(size_t)r * lds + c] : 0.0;
+}
+
+int tril_copy_f64(const double* src, int lds, double* dst, int ldd, int n, cudaStream_t st) {
+  dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n, 8));
+  tril_copy_kernel<<<grd, blk, 0, st>>>(src, lds, dst, ldd, n);
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
 }

@@ -149,6 +149,15 @@ class Stationary(Kern):
         X, X2 = self._slice(X, X2)
         return ops.kcore(X, X2, self.lengthscales, self._mode, float(jitter) if X2 is None else 0.0)
 
+    def Cholesky_factor(self, X):
+        """chol(core + jitter I) through the fused build-and-factor op (lower triangle only, in
+        place); its reverse reduces the blocked sweep's lower triangle straight into d/d(lengthscales)."""
+        if type(self)._Kcore is not Stationary._Kcore:
+            return Kern.Cholesky_factor(self, X)      # a subclass with its own core: generic path
+        Xs, _ = self._slice(X, None)
+        chol, info = ops.chol_core(Xs, self.lengthscales, self._mode, float(settings.numerics.jitter_level))
+        return CholeskyFactor([chol], torch.sqrt(self.variance), [0] * self.output_dim, [info])
+
     def __str__(self):
         return Parameterized.__str__(self)
 

@@ -163,6 +163,64 @@ def _potrf_backward(ctx, Lbar, _info_bar):
 potrf.register_autograd(_potrf_backward, setup_context=_potrf_setup)
 
 
+# --------------------------------------------------------------------------------------
+# T1-T4 fused: chol(core(X,X) + jitter I) with the lower-triangle-only build and reverse
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("gpinv::chol_core", mutates_args=(), device_types="cuda")
+def chol_core(X: Tensor, ls: Tensor, mode: int, jitter: float) -> Tuple[Tensor, Tensor]:
+    """(L, info) = Cholesky factor of core(X,X) + jitter*I (GPinv/kernels.py:56-59) in one call:
+    only the lower triangle of the core is evaluated and it is factored in place."""
+    X = _chk(X, "X")
+    ls = _chk(ls, "ls").reshape(-1)
+    ensure_workspace(X.device)
+    n, D = X.shape
+    ard = 1 if ls.numel() > 1 else 0
+    Lm = torch.empty((n, n), dtype=torch.float64, device=X.device)
+    info = torch.zeros(2, dtype=torch.int32, device=X.device)
+    lib = _capi.lib()
+    ws = _ws(lib.gpinv_chol_core_ws_bytes(n, D), X)
+    rc = lib.gpinv_chol_core_f64(_p(X), n, D, D, _p(ls), ard, mode, float(jitter), _p(Lm), n, _p(info),
+                                 _p(ws), _st())
+    _capi.check(rc, "chol_core")
+    return Lm, info
+
+
+@torch.library.custom_op("gpinv::chol_core_bwd", mutates_args=(), device_types="cuda")
+def chol_core_bwd(X: Tensor, ls: Tensor, mode: int, L: Tensor, Lbar: Tensor) -> Tensor:
+    """dObj/d(lengthscales) from dObj/dL: blocked Cholesky reverse sweep kept as a lower triangle
+    and reduced straight into the lengthscale gradient (no symmetric n x n gradient is formed)."""
+    X = _chk(X, "X")
+    ls = _chk(ls, "ls").reshape(-1)
+    L = _chk(L, "L")
+    Lbar = _chk(Lbar, "Lbar")
+    ensure_workspace(X.device)
+    n, D = X.shape
+    ard = 1 if ls.numel() > 1 else 0
+    out = torch.empty_like(ls)
+    lib = _capi.lib()
+    ws = _ws(lib.gpinv_chol_core_bwd_ws_bytes(n, D), X)
+    rc = lib.gpinv_chol_core_bwd_f64(_p(X), n, D, D, _p(ls), ard, mode, _p(L), n, _p(Lbar), n, _p(out),
+                                     _p(ws), _st())
+    _capi.check(rc, "chol_core_bwd")
+    return out
+
+
+def _chol_core_setup(ctx, inputs, output):
+    X, ls, mode, jitter = inputs
+    ctx.save_for_backward(X, ls, output[0])
+    ctx.mode = mode
+    ctx.ls_shape = ls.shape
+
+
+def _chol_core_backward(ctx, Lbar, _info_bar):
+    X, ls, L = ctx.saved_tensors
+    g = chol_core_bwd(X, ls, ctx.mode, L, Lbar.contiguous())
+    return None, g.reshape(ctx.ls_shape), None, None
+
+
+chol_core.register_autograd(_chol_core_backward, setup_context=_chol_core_setup)
+
+
 @torch.library.custom_op("gpinv::trsm_rlt", mutates_args=(), device_types="cuda")
 def trsm_rlt(L: Tensor, B: Tensor) -> Tensor:
     """X = B L^{-T} (B is [m,n]); i.e. every row x solves L x = b.  GPinv/conditionals.py:44."""

@@ -65,6 +65,21 @@ int gpinv_potrf_f64(double* A, int n, int lda, int* info, void* stream);
 size_t gpinv_potrf_bwd_ws_bytes(int n);
 int gpinv_potrf_bwd_f64(const double* L, int ldl, double* Abar, int ldab, int n, void* ws,
                         void* stream);
+
+/* --- T1-T4 fused: L = chol(core(X,X) + jitter I) and its reverse.  Replaces the whole body of
+ * Kern.Cholesky up to the variance scaling (GPinv/kernels.py:56-59: _Kcore + eye*jitter +
+ * tf.cholesky) and, in reverse, TF's CholeskyGrad followed by the gradient of _Kcore w.r.t. the
+ * lengthscales.  Only the lower triangle of the core is ever evaluated; the reverse keeps the
+ * blocked sweep's lower-triangular result (strict part doubled) and reduces it straight into
+ * ls_bar [D if ard else 1], so no symmetric n x n gradient is materialised.  L [n,n] receives a
+ * clean lower-triangular factor; info as in gpinv_potrf_f64. */
+size_t gpinv_chol_core_ws_bytes(int n, int D);
+int gpinv_chol_core_f64(const double* X, int n, int D, int ldx, const double* ls, int ard, int mode,
+                        double jitter, double* L, int ldl, int* info, void* ws, void* stream);
+size_t gpinv_chol_core_bwd_ws_bytes(int n, int D);
+int gpinv_chol_core_bwd_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
+                            int mode, const double* L, int ldl, const double* Lbar, int ldlb,
+                            double* ls_bar, void* ws, void* stream);
 /* --- T22: X <- X L^{-T} (row-wise forward substitution; X is m x n).  Replaces
  * tf.batch_matrix_triangular_solve at GPinv/conditionals.py:44 (applied to Kmn^T). */
 int gpinv_trsm_rlt_f64(const double* L, int ldl, double* X, int ldx, int m, int n, void* stream);
