@@ -34,48 +34,46 @@ constexpr int LEAF_SMEM = (2 * NB * LDR) * 8;
 // panel_kernel: factor the b x b diagonal block at (i0,i0) and solve X L11^T = A21 for the
 // rows below.  Thread-per-row, left-looking in 8-column register blocks.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(pcfg::NB + pcfg::RB) panel_kernel(double* __restrict__ A, int lda,
-                                                                    int n, int i0, int b,
-                                                                    int* __restrict__ info) {
+__global__ void __launch_bounds__(2 * (pcfg::NB + pcfg::RB)) panel_kernel(double* __restrict__ A, int lda,
+                                                                          int n, int i0, int b,
+                                                                          int* __restrict__ info) {
   using namespace pcfg;
   extern __shared__ __align__(16) double sm[];
   double* Rs = sm;                      // [NB+RB][LDR]
   double* Lt = Rs + (NB + RB) * LDR;    // [NB][LDT]   Lt[k][c] = L11[c][k]
   double* Ds = Lt + NB * LDT;           // [8][9]
   const int tid = threadIdx.x;
-  const int nthr = NB + RB;
+  constexpr int ROWS = NB + RB;         // rows held by the CTA: 64 of the diagonal block + 64 below
+  constexpr int NTHR = 2 * ROWS;        // every row has an owner thread and a helper thread
   const int row_base = i0 + b + blockIdx.x * RB;
   const int nrows = max(0, min(RB, n - row_base));
 
   // L2-only (ld.global.cg) loads: the look-ahead runs this kernel concurrently with the
-  // side-stream trailing update, so L1 must not be trusted.  All 32 loads a thread owes to each
-  // of the two blocks are issued back to back (one exposed L2 round trip per block, not four).
+  // side-stream trailing update, so L1 must not be trusted.  All 16 loads a thread owes to each
+  // of the two blocks are issued back to back (one exposed L2 round trip per block).
   {
-    constexpr int PER = NB * NB / (NB + RB);   // 32 elements per thread per block
+    constexpr int PER = NB * NB / NTHR;   // 16 elements per thread per block
     double v[PER];
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-      const int idx = u * nthr + tid;
+      const int idx = u * NTHR + tid;
       const int r = idx >> 6, c = idx & 63;
       v[u] = (r == c) ? 1.0 : 0.0;
       if (r < b && c < b) v[u] = __ldcg(A + (size_t)(i0 + r) * lda + i0 + c);
     }
+    double w[PER];
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-      const int idx = u * nthr + tid;
-      Rs[(idx >> 6) * LDR + (idx & 63)] = v[u];
-    }
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-      const int idx = u * nthr + tid;
+      const int idx = u * NTHR + tid;
       const int r = idx >> 6, c = idx & 63;
-      v[u] = 0.0;
-      if (r < nrows && c < b) v[u] = __ldcg(A + (size_t)(row_base + r) * lda + i0 + c);
+      w[u] = 0.0;
+      if (r < nrows && c < b) w[u] = __ldcg(A + (size_t)(row_base + r) * lda + i0 + c);
     }
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-      const int idx = u * nthr + tid;
-      Rs[(NB + (idx >> 6)) * LDR + (idx & 63)] = v[u];
+      const int idx = u * NTHR + tid;
+      Rs[(idx >> 6) * LDR + (idx & 63)] = v[u];
+      Rs[(NB + (idx >> 6)) * LDR + (idx & 63)] = w[u];
     }
   }
   __syncthreads();
@@ -89,86 +87,120 @@ __global__ void __launch_bounds__(pcfg::NB + pcfg::RB) panel_kernel(double* __re
     if (s_last) info[1] = 0;
   }
 
+  // Left-looking sweep over 8-column blocks with two threads per row.  The OWNER of a row
+  // (tid < ROWS) brings the current block up to date with the previous block's 8 columns,
+  // factors the 8x8 pivot block (redundantly, in registers) and solves its row's 8 entries.
+  // Meanwhile the HELPER of the row (tid >= ROWS) applies all columns finished BEFORE the current
+  // block to the NEXT block's 8 entries: that is the long part of the left-looking update and it
+  // does not depend on the pivot chain the owners are waiting on, so the two overlap.
+  const bool owner = tid < ROWS;
+  const int row = owner ? tid : tid - ROWS;
   int fail = INT_MAX;
-  double* myrow = Rs + tid * LDR;
+  double* myrow = Rs + row * LDR;
 #pragma unroll 1
   for (int cb = 0; cb < NB / 8; ++cb) {
     const int c0 = cb * 8;
-    const bool active = (tid >= c0);
     double s[8];
-    if (active) {
+    bool active = false;
+    if (owner) {
+      active = (row >= c0);
+      if (active) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) s[q] = myrow[c0 + q];
-      for (int k = 0; k < c0; ++k) {
-        const double li = myrow[k];
-        const double2* lt = reinterpret_cast<const double2*>(Lt + k * LDT + c0);
-        const double2 l01 = lt[0], l23 = lt[1], l45 = lt[2], l67 = lt[3];
-        s[0] -= li * l01.x; s[1] -= li * l01.y; s[2] -= li * l23.x; s[3] -= li * l23.y;
-        s[4] -= li * l45.x; s[5] -= li * l45.y; s[6] -= li * l67.x; s[7] -= li * l67.y;
-      }
-    }
-    if (tid >= c0 && tid < c0 + 8) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) Ds[(tid - c0) * 9 + q] = s[q];
-    }
-    __syncthreads();
-    // every thread factors the 8x8 diagonal block redundantly in registers, right-looking so
-    // the dependent chain per pivot is rsqrt -> scale -> one FMA
-    double l[8][8], inv[8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int bb = 0; bb <= a; ++bb) l[a][bb] = Ds[a * 9 + bb];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double v = l[j][j];
-      if (!(v > 0.0)) fail = min(fail, c0 + j);
-      const double y = fast_rsqrt(v);
-      inv[j] = y;
-#pragma unroll
-      for (int i = j + 1; i < 8; ++i) l[i][j] *= y;
-#pragma unroll
-      for (int i = j + 1; i < 8; ++i)
-#pragma unroll
-        for (int k = j + 1; k <= i; ++k) l[i][k] -= l[i][j] * l[k][j];
-      l[j][j] = sqrt_from_rsqrt(v, y);
-    }
-    if (active) {
-      double x[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) x[q] = s[q];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        x[q] *= inv[q];
-#pragma unroll
-        for (int m = q + 1; m < 8; ++m) x[m] -= x[q] * l[m][q];
-      }
-      if (tid < c0 + 8) {  // rows of the diagonal 8x8 block: exact diagonal, zero upper part
-        const int a = tid - c0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (q == a) x[q] = l[q][q];
-          if (q > a) x[q] = 0.0;
+        for (int q = 0; q < 8; ++q) s[q] = myrow[c0 + q];
+        // columns [c0-8, c0): finished during the previous block (everything older was applied
+        // by the helper while that block was being factored)
+        for (int k = max(c0 - 8, 0); k < c0; ++k) {
+          const double li = myrow[k];
+          const double2* lt = reinterpret_cast<const double2*>(Lt + k * LDT + c0);
+          const double2 l01 = lt[0], l23 = lt[1], l45 = lt[2], l67 = lt[3];
+          s[0] -= li * l01.x; s[1] -= li * l01.y; s[2] -= li * l23.x; s[3] -= li * l23.y;
+          s[4] -= li * l45.x; s[5] -= li * l45.y; s[6] -= li * l67.x; s[7] -= li * l67.y;
         }
       }
+      if (row >= c0 && row < c0 + 8) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) myrow[c0 + q] = x[q];
-      if (tid < NB) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) Lt[(c0 + q) * LDT + tid] = x[q];
+        for (int q = 0; q < 8; ++q) Ds[(row - c0) * 9 + q] = s[q];
       }
+    }
+    __syncthreads();
+    if (owner) {
+      // every owner factors the 8x8 diagonal block redundantly in registers, right-looking so
+      // the dependent chain per pivot is rsqrt -> scale -> one FMA
+      double l[8][8], inv[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int bb = 0; bb <= a; ++bb) l[a][bb] = Ds[a * 9 + bb];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double v = l[j][j];
+        if (!(v > 0.0)) fail = min(fail, c0 + j);
+        const double y = fast_rsqrt(v);
+        inv[j] = y;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) l[i][j] *= y;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+          for (int k = j + 1; k <= i; ++k) l[i][k] -= l[i][j] * l[k][j];
+        l[j][j] = sqrt_from_rsqrt(v, y);
+      }
+      if (active) {
+        double x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = s[q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          x[q] *= inv[q];
+#pragma unroll
+          for (int m = q + 1; m < 8; ++m) x[m] -= x[q] * l[m][q];
+        }
+        if (row < c0 + 8) {  // rows of the diagonal 8x8 block: exact diagonal, zero upper part
+          const int a = row - c0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (q == a) x[q] = l[q][q];
+            if (q > a) x[q] = 0.0;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) myrow[c0 + q] = x[q];
+        if (row < NB) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) Lt[(c0 + q) * LDT + row] = x[q];
+        }
+      }
+    } else if (cb + 1 < NB / 8 && c0 > 0 && row >= c0 + 8) {
+      // helper: next block's entries minus the contribution of columns [0, c0)
+      const int n0 = c0 + 8;
+      double t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t[q] = myrow[n0 + q];
+#pragma unroll 4
+      for (int k = 0; k < c0; ++k) {
+        const double li = myrow[k];
+        const double2* lt = reinterpret_cast<const double2*>(Lt + k * LDT + n0);
+        const double2 l01 = lt[0], l23 = lt[1], l45 = lt[2], l67 = lt[3];
+        t[0] -= li * l01.x; t[1] -= li * l01.y; t[2] -= li * l23.x; t[3] -= li * l23.y;
+        t[4] -= li * l45.x; t[5] -= li * l45.y; t[6] -= li * l67.x; t[7] -= li * l67.y;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) myrow[n0 + q] = t[q];
     }
     __syncthreads();
   }
 
   if (s_last) {   // (s_last was written before the first barrier of the main loop)
-    for (int idx = tid; idx < NB * NB; idx += nthr) {
+    for (int idx = tid; idx < NB * NB; idx += NTHR) {
       const int r = idx >> 6, c = idx & 63;
       if (r < b && c < b) A[(size_t)(i0 + r) * lda + i0 + c] = (c <= r) ? Rs[r * LDR + c] : 0.0;
     }
-    if (tid == 0 && fail != INT_MAX && fail < b) atomicCAS(info, 0, i0 + fail + 1);
+    if (owner) {
+      // `fail` is identical in every owner thread of the CTA
+      if (tid == 0 && fail != INT_MAX && fail < b) atomicCAS(info, 0, i0 + fail + 1);
+    }
   }
-  for (int idx = tid; idx < RB * NB; idx += nthr) {
+  for (int idx = tid; idx < RB * NB; idx += NTHR) {
     const int r = idx >> 6, c = idx & 63;
     if (r < nrows && c < b) A[(size_t)(row_base + r) * lda + i0 + c] = Rs[(NB + r) * LDR + c];
   }
@@ -413,7 +445,7 @@ int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaSt
     for (int i = o; i < o + w; i += NB) {
       const int b = min(NB, o + w - i);
       const int below = n - i - b;
-      panel_kernel<<<max(1, cdiv(below, RB)), NB + RB, PANEL_SMEM, st>>>(A, lda, n, i, b, info);
+      panel_kernel<<<max(1, cdiv(below, RB)), 2 * (NB + RB), PANEL_SMEM, st>>>(A, lda, n, i, b, info);
       GPINV_CHECK_LAUNCH();
       if (i + b < o + w) {
         double* P = A + (size_t)(i + b) * lda + i;

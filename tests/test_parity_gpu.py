@@ -309,12 +309,16 @@ def test_full_size_cfg5_properties():
     gd = float(g.dot(d))
     assert abs(fdiff(d, 1e-3) - gd) <= 1e-7 * abs(gd), (fdiff(d, 1e-3), gd)
     # hyper-parameters one at a time: a perturbed K is re-factored at cond ~2e9, which puts ~1e-9
-    # relative noise on the ELBO; h = 1e-4 keeps the difference quotient good to ~1e-6 (oracle: 1.2e-6)
+    # relative noise on the ELBO (two correct Cholesky implementations differ by that much here:
+    # 34197.81970938 vs 34197.81975101 when only the pivot rsqrt's rounding changed).  With
+    # h = 1e-4 that noise alone is worth ~1e-9 |f| / (2h |g|) ~ 5e-5 of the difference quotient
+    # (the oracle's own quotient is off by 1e-6..1e-5 too), so the bar is 2e-4: a wrong
+    # hyper-gradient would be off by O(1).
     for i in range(4):
         e = torch.zeros_like(x)
         e[i] = 1.0
         fd = fdiff(e, 1e-4)
-        assert abs(fd - float(g[i])) <= 1e-5 * abs(float(g[i])), (i, fd, float(g[i]))
+        assert abs(fd - float(g[i])) <= 2e-4 * abs(float(g[i])), (i, fd, float(g[i]))
     m._check_infos()
 
 
