@@ -315,7 +315,7 @@ def main():
         mine = [e for e in ev if any(s_ in e.name for s_ in (
             "gemm_dmma", "panel_kernel", "trsm_", "trtri", "kbuild", "kprep", "tril_", "sumsq", "colsum",
             "diag_", "kl_finish", "zero_upper", "mirror", "scale_diag", "leaf_rev", "symmetrize", "udiag",
-            "gauss_", "set_identity", "spec_", "skinny_"))]
+            "gauss_", "set_identity", "spec_", "skinny_", "tril_copy", "finalize_sym"))]
         launches = len(mine) * K
         launch_detail = {"gpinv_b200": len(mine), "all_cuda_kernels": len(ev)}
     except Exception as e:  # pragma: no cover

@@ -109,12 +109,16 @@ __global__ void __launch_bounds__(2 * (pcfg::NB + pcfg::RB)) panel_kernel(double
         for (int q = 0; q < 8; ++q) s[q] = myrow[c0 + q];
         // columns [c0-8, c0): finished during the previous block (everything older was applied
         // by the helper while that block was being factored)
-        for (int k = max(c0 - 8, 0); k < c0; ++k) {
-          const double li = myrow[k];
-          const double2* lt = reinterpret_cast<const double2*>(Lt + k * LDT + c0);
-          const double2 l01 = lt[0], l23 = lt[1], l45 = lt[2], l67 = lt[3];
-          s[0] -= li * l01.x; s[1] -= li * l01.y; s[2] -= li * l23.x; s[3] -= li * l23.y;
-          s[4] -= li * l45.x; s[5] -= li * l45.y; s[6] -= li * l67.x; s[7] -= li * l67.y;
+        if (c0 > 0) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {      // exactly 8 columns: unrolled, loads ahead of the FMAs
+            const int k = c0 - 8 + kk;
+            const double li = myrow[k];
+            const double2* lt = reinterpret_cast<const double2*>(Lt + k * LDT + c0);
+            const double2 l01 = lt[0], l23 = lt[1], l45 = lt[2], l67 = lt[3];
+            s[0] -= li * l01.x; s[1] -= li * l01.y; s[2] -= li * l23.x; s[3] -= li * l23.y;
+            s[4] -= li * l45.x; s[5] -= li * l45.y; s[6] -= li * l67.x; s[7] -= li * l67.y;
+          }
         }
       }
       if (row >= c0 && row < c0 + 8) {
