@@ -174,17 +174,20 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
     struct PlanKey { int M, N, K, kmode, lower, batch; };
     static thread_local PlanKey cache_key[64];
     static thread_local int cache_val[64];
+    static thread_local int cache_from[64];
     static thread_local int cache_n = 0;
-    int cached = -1;
+    int cached = -1, cached_from = 0;
     for (int i = 0; i < cache_n; ++i) {
       const PlanKey& c = cache_key[i];
       if (c.M == p.M && c.N == p.N && c.K == p.K && c.kmode == p.kmode && c.lower == (int)lower && c.batch == p.batch) {
         cached = cache_val[i];
+        cached_from = cache_from[i];
         break;
       }
     }
     if (w && cached > 1) {
       p.splitk = cached;
+      p.split_from = cached_from;
       p.ws_cnt = static_cast<int*>(w->ptr);
       p.ws = reinterpret_cast<double*>(static_cast<char*>(w->ptr) + CNT_SLOTS * sizeof(int));
     } else if (w && cached < 0 && T <= CNT_SLOTS / 2 && T1 <= 4096) {
@@ -198,16 +201,19 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
         kt[i] = (ke > kb) ? cdiv(ke - kb, 16) : 0;
       }
       const int sms = 148;
-      auto makespan = [&](int s_) {
+      auto makespan = [&](int s_, int from) {
         double busy[148];
         for (int i = 0; i < sms; ++i) busy[i] = 0.0;
-        // launch order: blockIdx.x fastest, then the slice index, then the batch
+        // launch order: blockIdx.x fastest, then the slice index, then the batch; tiles before
+        // `from` are not split (their extra slice CTAs exit immediately)
         for (int z = 0; z < p.batch; ++z)
           for (int y = 0; y < s_; ++y)
             for (int i = 0; i < T1; ++i) {
-              const int per = cdiv(kt[i], s_);
+              const int si = (i >= from) ? s_ : 1;
+              if (y >= si) continue;
+              const int per = cdiv(kt[i], si);
               const int mine = (kt[i] - y * per < per ? kt[i] - y * per : per);
-              const double t = (mine > 0 ? mine : 0) * 2.1 + 3.0 + (s_ > 1 ? 6.0 : 0.0);
+              const double t = (mine > 0 ? mine : 0) * 2.1 + 3.0 + (si > 1 ? 6.0 : 0.0);
               int best = 0;
               for (int q = 1; q < sms; ++q) if (busy[q] < busy[best]) best = q;
               busy[best] += t;
@@ -216,22 +222,36 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
         for (int i = 0; i < sms; ++i) if (busy[i] > mx) mx = busy[i];
         return mx;
       };
-      double best = makespan(1);
-      int best_s = 1;
+      const double base = makespan(1, 0);
+      double best = base;
+      int best_s = 1, best_from = 0;
       int kt_max = 0;
       for (int i = 0; i < T1; ++i) if (kt[i] > kt_max) kt_max = kt[i];
       for (int s_ = 2; s_ <= 6; ++s_) {
         if (kt_max / s_ < 12 || (size_t)(T * s_) > cap) break;
-        const double c = makespan(s_);
-        if (c < 0.97 * best) { best = c; best_s = s_; }
+        const double c = makespan(s_, 0);
+        if (c < 0.97 * best) { best = c; best_s = s_; best_from = 0; }
+        // tail-wave split: with uniform tiles only the last (T mod 148) tiles need splitting;
+        // same makespan, a fraction of the slice exchange through the workspace
+        if (p.kmode == 0 && !lower && p.batch == 1 && T1 > sms && T1 % sms != 0) {
+          const int from = (T1 / sms) * sms;
+          const double ct = makespan(s_, from);
+          if (ct < 0.97 * base && ct <= 1.005 * best) {
+            best = (ct < best ? ct : best);
+            best_s = s_;
+            best_from = from;
+          }
+        }
       }
       if ((size_t)(T * best_s) > cap) best_s = 1;
       if (cache_n < 64) {
         cache_key[cache_n] = PlanKey{p.M, p.N, p.K, p.kmode, (int)lower, p.batch};
+        cache_from[cache_n] = best_from;
         cache_val[cache_n++] = best_s;
       }
       if (best_s > 1) {
         p.splitk = best_s;
+        p.split_from = best_from;
         p.ws_cnt = static_cast<int*>(w->ptr);
         p.ws = reinterpret_cast<double*>(static_cast<char*>(w->ptr) + CNT_SLOTS * sizeof(int));
       }
@@ -263,8 +283,8 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
   }
   static const bool log_gemm = (getenv("GPINV_GEMM_LOG") != nullptr);
   if (log_gemm)
-    fprintf(stderr, "gemm-log la=%d lb=%d ef=%u M=%d N=%d K=%d kmode=%d splitk=%d batch=%d cfg=%s\n", la, lb, ef,
-            p.M, p.N, p.K, p.kmode, p.splitk, p.batch, small ? "small" : "big");
+    fprintf(stderr, "gemm-log la=%d lb=%d ef=%u M=%d N=%d K=%d kmode=%d splitk=%d batch=%d cfg=%s from=%d\n", la, lb, ef,
+            p.M, p.N, p.K, p.kmode, p.splitk, p.batch, small ? "small" : "big", p.split_from);
   if (small) return dispatch<CfgSmall>(la, lb, ef, p, stream);
   static const int big_bk = getenv("GPINV_BIG_BK") ? atoi(getenv("GPINV_BIG_BK")) : 16;
   if (big_bk == 32 || p.force_cfg == 3) return dispatch<CfgBig32>(la, lb, ef, p, stream);

@@ -64,6 +64,7 @@ struct GemmParams {
   // counter, and the LAST arriver sums the slices in fixed order (deterministic) and runs the
   // fused epilogue.  No CTA ever waits on another.  Enabled per call with allow_split.
   int allow_split;
+  int split_from;   // k-split applies to tiles with index >= split_from only (tail-wave split)
   double* ws;
   int* ws_cnt;
   int vecA, vecB, vecO;  // 16-byte alignment of operands / output rows
@@ -291,8 +292,11 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& pin, const int 
   int kb, ke;
   gemm_krange(p.kmode, p.K, m0, n0, BM, BN, BK, kb, ke);
   int ktiles = (ke > kb) ? (ke - kb + BK - 1) / BK : 0;
-  if (p.splitk > 1) {
-    const int per = (ktiles + p.splitk - 1) / p.splitk;
+  // slices of THIS tile: tiles before split_from run unsplit (their extra slice CTAs exit at once)
+  const int nsl = (p.splitk > 1 && tile_x >= p.split_from) ? p.splitk : 1;
+  if ((int)blockIdx.y >= nsl) return;
+  if (nsl > 1) {
+    const int per = (ktiles + nsl - 1) / nsl;
     const int first = blockIdx.y * per;
     const int last = min(ktiles, first + per);
     kb += first * BK;
@@ -365,7 +369,7 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& pin, const int 
   cp_async_wait<0>();
 
   // ---- workspace split-K: combine the k-slices of this tile ----
-  if (!(EF & EF_ATOMIC) && p.splitk > 1) {
+  if (!(EF & EF_ATOMIC) && nsl > 1) {
     const size_t tile_id = (size_t)blockIdx.z * p.ntiles + tile_x;
     constexpr int TILE = BM * BN;
     double* mine = p.ws + (tile_id * p.splitk + blockIdx.y) * TILE;
@@ -381,7 +385,7 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& pin, const int 
     int* s_ticket = reinterpret_cast<int*>(smem);
     if (tid == 0) *s_ticket = atomicAdd(p.ws_cnt + tile_id, 1);
     __syncthreads();
-    if (*s_ticket != p.splitk - 1) return;
+    if (*s_ticket != nsl - 1) return;
     if (tid == 0) p.ws_cnt[tile_id] = 0;   // ready for the next launch (stream ordered)
     __threadfence();
     const double* base = p.ws + tile_id * p.splitk * TILE + tid;
@@ -390,7 +394,7 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& pin, const int 
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     // slices in fixed order (bitwise reproducible); all loads of one slice are independent
-    for (int sl = 0; sl < p.splitk; ++sl) {
+    for (int sl = 0; sl < nsl; ++sl) {
       const double* src = base + (size_t)sl * TILE;
 #pragma unroll
       for (int i = 0; i < TM; ++i) {
