@@ -296,8 +296,8 @@ def main():
         ach = 2.0 * Sl * n * M / tk / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_dmma_kernel<LK,LK,COLVEC|SUMSQ> (Abel transform R = y - exp(F) A^T)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": (628.8e6 if (world == 1 and args.config == "cfg5") else None),
-                "traffic_note": "dram__bytes_read+write per launch from profiles/r1_abel_gemm_ncu_full.txt (369 MB algorithmic operands+result, rest = split-K slice exchange)",
+                "traffic": (468.5e6 if (world == 1 and args.config == "cfg5") else None),
+                "traffic_note": "dram__bytes_read+write per launch from profiles/r1_abel_gemm_ncu_full.txt (403 MB algorithmic operands+result incl. the fused exp(F) read; rest = slice exchange of the tail-wave k-split)",
                 "peak_source": "cuBLAS DGEMM 4096^3 best-of-6 measured in this run (fp64 DMMA; MEASURED_PEAKS.json has no fp64 figure)",
                 "whole_eval_achieved": work_flops(n, M, S, world) / t_dev * K / 1e12,
                 "whole_eval_frac": work_flops(n, M, S, world) / t_dev * K / 1e12 / peak}
