@@ -320,6 +320,13 @@ def test_full_size_cfg5_properties():
         fd = fdiff(e, 1e-4)
         assert abs(fd - float(g[i])) <= 2e-4 * abs(float(g[i])), (i, fd, float(g[i]))
     m._check_infos()
+    # the benchmarked launch path: one replayed CUDA graph per evaluation (captures the Cholesky
+    # look-ahead stream, the forked reverse sweep and the CTA-capped persistent GEMM)
+    m.enable_cuda_graph()
+    for _ in range(2):
+        fg, gg = m._objective_device(x, eps=eps)
+        assert same_evaluation(float(fg), gg.cpu().numpy(), float(f), g.cpu().numpy(), 4)
+    m._check_infos()
 
 
 def test_predict_f_against_oracle():
