@@ -28,6 +28,7 @@ SIGNATURES = {
     "gpinv_last_error": (C.c_char_p, []),
     "gpinv_set_workspace": (_I, [_P, _Z]),
     "gpinv_memcpy2d_async": (_I, [_P, _Z, _P, _Z, _Z, _Z, _I, _P]),
+    "gpinv_upload_tril_blocks_f64": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
     "gpinv_kbuild_ws_bytes": (_Z, [_I, _I, _I]),
     "gpinv_kbuild_f64": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _D, _P, _I, _P, _P]),
     "gpinv_kbuild_bwd_f64": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P]),

@@ -1,7 +1,11 @@
 // extern "C" surface of libgpinv_sm100.so (declared in include/gpinv_b200.h).
+#include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/gpinv_b200.h"
 #include "gemm.cuh"
@@ -124,6 +128,68 @@ int gpinv_potrf_bwd_f64(const double* L, int ldl, double* Abar, int ldab, int n,
   if (mode == 0 && n > potrf_bwd_hybrid_block())
     return potrf_bwd_hybrid_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
   return potrf_bwd_inv_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
+}
+
+// ---- host side of the lower-trapezoid upload (Model._objective host boundary) ----
+// x_host: pageable row-major [nq,nq] matrix (q_sqrt inside the optimiser's state vector).  Row
+// blocks of `rb` rows are gathered -- columns [0, r1) of rows [r0, r1) -- into the pinned buffer at
+// element offset off[k] by `nthreads` worker threads (chunks of 8 rows, handed out in block
+// order), and the calling thread issues the block's contiguous host->device copy on `stream` as
+// soon as the block is complete.  Returns when every copy has been ISSUED.  take[k] == 0 skips a
+// block (another rank stages it).
+int gpinv_upload_tril_blocks_f64(const double* x_host, int nq, int rb, double* pinned, double* dstage,
+                                 const long long* off, const int* take, int nblocks, int nthreads,
+                                 void* stream) {
+  if (!x_host || !pinned || !dstage || !off || !take || nq <= 0 || rb <= 0 || nblocks <= 0) return GPINV_ERR_ARG;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+  constexpr int CH = 8;   // rows per work item
+  // work items in block order
+  std::vector<int> item_block, item_row;
+  std::vector<int> block_items(nblocks, 0);
+  for (int k = 0; k < nblocks; ++k) {
+    if (!take[k]) continue;
+    const int r0 = k * rb, r1 = (r0 + rb < nq) ? r0 + rb : nq;
+    for (int r = r0; r < r1; r += CH) {
+      item_block.push_back(k);
+      item_row.push_back(r);
+      ++block_items[k];
+    }
+  }
+  const int nitems = (int)item_block.size();
+  std::vector<std::atomic<int>> done(nblocks);
+  for (int k = 0; k < nblocks; ++k) done[k].store(0);
+  std::atomic<int> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      const int it = next.fetch_add(1);
+      if (it >= nitems) break;
+      const int k = item_block[it], ra = item_row[it];
+      const int r0 = k * rb, r1 = (r0 + rb < nq) ? r0 + rb : nq;
+      const int rz = (ra + CH < r1) ? ra + CH : r1;
+      const size_t width = (size_t)r1;                 // columns [0, r1)
+      for (int r = ra; r < rz; ++r)
+        std::memcpy(pinned + off[k] + (size_t)(r - r0) * width, x_host + (size_t)r * nq, width * sizeof(double));
+      done[k].fetch_add(1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> pool;
+  pool.reserve(nthreads);
+  for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+  int rc = GPINV_OK;
+  for (int k = 0; k < nblocks; ++k) {
+    if (!take[k]) continue;
+    while (done[k].load(std::memory_order_acquire) < block_items[k]) std::this_thread::sleep_for(std::chrono::microseconds(20));
+    const int r0 = k * rb, r1 = (r0 + rb < nq) ? r0 + rb : nq;
+    const size_t bytes = (size_t)(r1 - r0) * r1 * sizeof(double);
+    if (rc == GPINV_OK &&
+        cudaMemcpyAsync(dstage + off[k], pinned + off[k], bytes, cudaMemcpyHostToDevice, ST(stream)) != cudaSuccess) {
+      set_last_error(cudaGetErrorString(cudaGetLastError()));
+      rc = GPINV_ERR_CUDA;
+    }
+  }
+  for (auto& th : pool) th.join();
+  return rc;
 }
 
 // ---- fused kernel build + Cholesky (the Kern.Cholesky core of GPinv/kernels.py:56-59) ----

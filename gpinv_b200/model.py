@@ -293,15 +293,22 @@ class Model(Parameterized):
             else:
                 mine = set(range(len(blocks)))
 
+            offs_np = np.array([o_ for _, _, o_ in blocks], dtype=np.int64)
+            take_np = np.array([1 if k in mine else 0 for k in range(len(blocks))], dtype=np.int32)
+
             def upload_chunks():
-                for k, (r0, r1, o) in enumerate(blocks):
-                    if k not in mine:
-                        continue
-                    cnt = (r1 - r0) * r1
-                    st = hin[b0 + o:b0 + o + cnt].view(r1 - r0, r1)
-                    st.copy_(src2[r0:r1, :r1])                      # threaded strided host copy
-                    dstage[o:o + cnt].view(r1 - r0, r1).copy_(st, non_blocking=True)   # contiguous DMA
-                    state["h2d"] += 8 * cnt
+                # gather (pageable -> pinned, multi-threaded, GIL released) and per-block DMA are
+                # pipelined inside one native call
+                from . import _capi
+                nthr = max(1, min(8, torch.get_num_threads()))
+                rc = _capi.lib().gpinv_upload_tril_blocks_f64(
+                    x.ctypes.data + 8 * b0, nq, rb, hin.data_ptr() + 8 * b0, dstage.data_ptr(),
+                    offs_np.ctypes.data, take_np.ctypes.data, len(blocks), nthr,
+                    torch.cuda.current_stream().cuda_stream)
+                _capi.check(rc, "upload_tril_blocks")
+                for k, (r0, r1, o_) in enumerate(blocks):
+                    if k in mine:
+                        state["h2d"] += 8 * (r1 - r0) * r1
                 if G > 1:
                     self.dist.all_reduce(dstage)
                 for r0, r1, o in blocks:                            # strided scatter on the device

@@ -44,6 +44,16 @@ int gpinv_set_workspace(void* ptr, size_t bytes);
 int gpinv_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch,
                          size_t width_bytes, size_t height, int kind, void* stream);
 
+/* Host half of the same boundary, upload direction: x_host is the pageable row-major [nq,nq]
+ * q_sqrt block of the optimiser's state vector (GPinv/stvgp.py:71-73; only its lower triangle is
+ * read, :157).  Row blocks of rb rows are gathered (columns [0, r1) of rows [r0, r1)) into the
+ * pinned buffer at element offsets off[k] by nthreads host threads, and each block's contiguous
+ * host->device copy into dstage + off[k] is issued on `stream` as soon as the block is staged.
+ * take[k] == 0 skips block k.  Returns once every copy is issued (not completed). */
+int gpinv_upload_tril_blocks_f64(const double* x_host, int nq, int rb, double* pinned, double* dstage,
+                                 const long long* off, const int* take, int nblocks, int nthreads,
+                                 void* stream);
+
 /* --- T1-T3: kernel core matrix.  Replaces Kern._Kcore + jitter (GPinv/kernels.py:57-58,
  * 105-107,115-120,140-145; GPflow Stationary.square_dist).  X [n,D], X2 [n2,D] or NULL
  * (then K is n x n and `jitter` is added to its diagonal); ls device [D] (ard) or [1]. */
