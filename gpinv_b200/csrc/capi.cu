@@ -140,7 +140,8 @@ int gpinv_potrf_bwd_f64(const double* L, int ldl, double* Abar, int ldab, int n,
 int gpinv_upload_tril_blocks_f64(const double* x_host, int nq, int rb, double* pinned, double* dstage,
                                  const long long* off, const int* take, int nblocks, int nthreads,
                                  void* stream) {
-  if (!x_host || !pinned || !dstage || !off || !take || nq <= 0 || rb <= 0 || nblocks <= 0) return GPINV_ERR_ARG;
+  // dstage == NULL: gather only (no copies are issued; used by the CPU-side test of the packing)
+  if (!x_host || !pinned || !off || !take || nq <= 0 || rb <= 0 || nblocks <= 0) return GPINV_ERR_ARG;
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 64) nthreads = 64;
   constexpr int CH = 8;   // rows per work item
@@ -182,7 +183,7 @@ int gpinv_upload_tril_blocks_f64(const double* x_host, int nq, int rb, double* p
     while (done[k].load(std::memory_order_acquire) < block_items[k]) std::this_thread::sleep_for(std::chrono::microseconds(20));
     const int r0 = k * rb, r1 = (r0 + rb < nq) ? r0 + rb : nq;
     const size_t bytes = (size_t)(r1 - r0) * r1 * sizeof(double);
-    if (rc == GPINV_OK &&
+    if (rc == GPINV_OK && dstage &&
         cudaMemcpyAsync(dstage + off[k], pinned + off[k], bytes, cudaMemcpyHostToDevice, ST(stream)) != cudaSuccess) {
       set_last_error(cudaGetErrorString(cudaGetLastError()));
       rc = GPINV_ERR_CUDA;

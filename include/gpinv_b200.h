@@ -49,7 +49,8 @@ int gpinv_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitc
  * read, :157).  Row blocks of rb rows are gathered (columns [0, r1) of rows [r0, r1)) into the
  * pinned buffer at element offsets off[k] by nthreads host threads, and each block's contiguous
  * host->device copy into dstage + off[k] is issued on `stream` as soon as the block is staged.
- * take[k] == 0 skips block k.  Returns once every copy is issued (not completed). */
+ * take[k] == 0 skips block k.  Returns once every copy is issued (not completed).  dstage == NULL
+ * gathers only. */
 int gpinv_upload_tril_blocks_f64(const double* x_host, int nq, int rb, double* pinned, double* dstage,
                                  const long long* off, const int* take, int nblocks, int nthreads,
                                  void* stream);

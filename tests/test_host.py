@@ -52,6 +52,58 @@ def test_product_does_not_import_the_oracle():
             assert "import oracle" not in src and "from oracle" not in src, fn
 
 
+def test_native_trapezoid_gather_packs_the_lower_row_blocks():
+    """Host half of the q_sqrt upload (gpinv_upload_tril_blocks_f64 without a device target): block k
+    of rb rows lands at off[k] as a packed [rows, r1] matrix holding columns [0, r1); skipped blocks
+    are left untouched; ragged last block."""
+    lib = _capi.lib()
+    nq, rb = 300, 64
+    rng = np.random.RandomState(0)
+    x = rng.randn(nq * nq)
+    blocks, o = [], 0
+    for r0 in range(0, nq, rb):
+        r1 = min(nq, r0 + rb)
+        blocks.append((r0, r1, o))
+        o += (r1 - r0) * r1
+    off = np.array([b[2] for b in blocks], dtype=np.int64)
+    take = np.array([1, 0, 1, 1, 1], dtype=np.int32)
+    dst = np.full(o, -7.0)
+    rc = lib.gpinv_upload_tril_blocks_f64(x.ctypes.data, nq, rb, dst.ctypes.data, None, off.ctypes.data,
+                                          take.ctypes.data, len(blocks), 3, None)
+    assert rc == 0
+    X2 = x.reshape(nq, nq)
+    for k, (r0, r1, oo) in enumerate(blocks):
+        got = dst[oo:oo + (r1 - r0) * r1].reshape(r1 - r0, r1)
+        if take[k]:
+            assert np.array_equal(got, X2[r0:r1, :r1])
+        else:
+            assert np.all(got == -7.0)
+
+
+def test_make_tensors_with_a_separately_held_block():
+    """Parameterized.make_tensors(x, override=...): the pipelined host path keeps q_sqrt in its own
+    allocation; the remaining blocks are sliced from the packed rest in order."""
+    X = np.linspace(0, 1, 6)[:, None]
+    m = stvgp.StVGP(X, np.sin(X), kernels.RBF(1, 1), likelihoods.Gaussian())
+    x = m.get_free_state() + 0.1 * np.arange(m.get_free_state().size)
+    params = [p for p in m.all_params() if not p.fixed]
+    big = max(range(len(params)), key=lambda i: params[i].size)
+    sizes = [p.size for p in params]
+    b0 = sum(sizes[:big])
+    xt = torch.as_tensor(x)
+    rest = torch.cat([xt[:b0], xt[b0 + sizes[big]:]])
+    leaves_a = m.make_tensors(xt)
+    vals_a = [l.detach().clone().reshape(-1) for l in leaves_a]
+    m.clear_tensors()
+    leaves_b = m.make_tensors(rest, override={big: xt[b0:b0 + sizes[big]].clone()})
+    for a, b in zip(vals_a, leaves_b):
+        assert torch.equal(a, b.detach().reshape(-1))
+    m.clear_tensors()
+    with pytest.raises(ValueError):
+        m.make_tensors(rest, override={big: xt[:3].clone()})
+    m.clear_tensors()
+
+
 def test_positive_transform_roundtrip_and_offset():
     t = transforms.positive
     y = np.array([1e-5, 0.007, 0.3, 1.0, 50.0])
