@@ -35,7 +35,10 @@ GPflow 0.3 are not installable, but ``oracle/run_reference.py`` imports the unmo
 ``tests/golden/ref_*.npz`` (ELBO / log-density, packed gradient, ``predict_f`` mean / variance /
 full covariance, LOS matrices; 10 model cases incl. BASELINE configs[0]).  This restatement
 reproduces every one of them (``tests/test_oracle.py``: |df| <= 1e-9|f|, ||dg|| <= 1e-8||g||; measured
-<= 2e-11 and <= 1e-10).  The GPflow formulas themselves (not vendored in the reference) are pinned by
+<= 2e-11 and <= 1e-10).  The stand-ins themselves are validated by the reference's OWN unit tests:
+all 28 in-scope tests of ``testing/test_kernels.py``, ``test_kronecker.py``, ``test_mean.py``,
+``test_stvgp.py`` (incl. the optimisation against exact GP regression) and ``test_gpmc.py`` pass
+when run over them (``python -m oracle.run_reference_tests``).  The GPflow formulas themselves (not vendored in the reference) are pinned by
 (G1) the golden value published in ``notebooks/Stochastic_approximation_demo.ipynb:142-150``
 (19.49947035345194), which fixes the RBF formula, density constants, softplus+1e-6 transform
 and parameter order; further checks: (G2) the zero-variance identity ELBO_MC == log p(Y) for the

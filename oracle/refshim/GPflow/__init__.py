@@ -3,4 +3,4 @@ subclasses or calls.  TEST INFRASTRUCTURE ONLY -- see oracle/refshim/README.md. 
 un-vendored, unpinned dependency of the reference (setup.py:33), so these modules restate its
 published behaviour; they contain no GPinv logic."""
 from . import _settings, scoping, transforms, densities, tf_wraps, priors, param  # noqa: F401
-from . import kullback_leiblers, kernels, likelihoods, mean_functions, model, gpmc  # noqa: F401
+from . import kullback_leiblers, kernels, likelihoods, mean_functions, model, gpmc, gpr, hmc  # noqa: F401

@@ -62,3 +62,11 @@ class Stationary(Kern):
 
     def Kdiag(self, X):
         return self.variance * tf.ones((tf.shape(X)[0],), tf.float64)
+
+
+class RBF(Stationary):
+    """GPflow's own (single-output) RBF kernel: variance * exp(-d^2 / 2)."""
+
+    def K(self, X, X2=None):
+        X, X2 = self._slice(X, X2)
+        return self.variance * tf.exp(-self.square_dist(X, X2) / 2)

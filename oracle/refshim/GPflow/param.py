@@ -169,6 +169,9 @@ class Parameterized(Parentable):
         return count
 
     def make_tf_array(self, X):
+        if isinstance(X, np.ndarray):      # the reference's tests pass the numpy free state directly
+            import torch
+            X = torch.as_tensor(X, dtype=torch.float64)
         count = 0
         for p in self.sorted_params:
             count += p.make_tf_array(X[count:])
@@ -179,6 +182,10 @@ class Parameterized(Parentable):
         for p in self.sorted_params:
             total = total + p.build_prior()
         return total
+
+    def get_feed_dict(self):
+        """GPflow fed DataHolder placeholders through this dict; data are constants here."""
+        return {}
 
     @contextmanager
     def tf_mode(self):

@@ -14,12 +14,17 @@ int32 = torch.int32
 __version__ = "0.10.0-refshim"
 
 _RANDOM_NORMAL_QUEUE = []
+_STRICT = [False]
+_AUTO_GEN = [torch.Generator().manual_seed(0)]
 
 
-def set_random_normal_queue(draws):
-    """Pre-set the values the next ``tf.random_normal`` calls return (in call order)."""
+def set_random_normal_queue(draws, strict=True):
+    """Pre-set the values the next ``tf.random_normal`` calls return (in call order).  With
+    ``strict`` (fixture generation) a call that finds the queue empty is an error; otherwise it
+    draws from the module generator like the real op would (optimisation, sampling)."""
     del _RANDOM_NORMAL_QUEUE[:]
     _RANDOM_NORMAL_QUEUE.extend(draws)
+    _STRICT[0] = bool(strict)
 
 
 def random_normal_queue_len():
@@ -213,7 +218,9 @@ batch_cholesky = cholesky
 def random_normal(shp, mean=0.0, stddev=1.0, dtype=float32, seed=None, name=None):
     shp = tuple(int(s) for s in shp)
     if not _RANDOM_NORMAL_QUEUE:
-        raise RuntimeError("tf.random_normal%r called with an empty draw queue" % (shp,))
+        if _STRICT[0]:
+            raise RuntimeError("tf.random_normal%r called with an empty draw queue" % (shp,))
+        return mean + stddev * torch.randn(shp, dtype=torch.float64, generator=_AUTO_GEN[0])
     draw = _t(_RANDOM_NORMAL_QUEUE.pop(0))
     if tuple(draw.shape) != shp:
         raise ValueError("queued draw has shape %r, the graph asks for %r" % (tuple(draw.shape), shp))
@@ -233,3 +240,43 @@ nn = _NN()
 
 def gradients(ys, xs):
     return list(torch.autograd.grad(ys, xs, allow_unused=True))
+
+
+# ---- session plumbing of the reference's own tests (testing/test_kernels.py etc.): eager here ----
+class Session(object):
+    def run(self, fetches, feed_dict=None):
+        def one(v):
+            return v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        if isinstance(fetches, (list, tuple)):
+            return [one(v) for v in fetches]
+        return one(fetches)
+
+    def close(self):
+        pass
+
+
+def initialize_all_variables():
+    return None
+
+
+def set_random_seed(seed):
+    torch.manual_seed(int(seed))
+    _AUTO_GEN[0] = torch.Generator().manual_seed(int(seed))
+
+
+class _AdamOptimizer(object):
+    """tf.train.AdamOptimizer: the hyper-parameters only; GPflow.model.Model.optimize applies them."""
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        self.learning_rate, self.beta1, self.beta2, self.epsilon = learning_rate, beta1, beta2, epsilon
+
+
+class _Train(object):
+    AdamOptimizer = _AdamOptimizer
+
+
+train = _Train()
+
+
+def ones_initializer(*a, **k):          # pragma: no cover  (name only)
+    raise NotImplementedError

@@ -206,3 +206,16 @@ def test_reference_runner_reproduces_committed_fixtures():
     r = subprocess.run([sys.executable, "-W", "ignore", "-m", "oracle.run_reference", "--check"], cwd=root,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/testing"), reason="reference sources only exist in the build container")
+def test_reference_own_unit_tests_pass_over_the_shim():
+    """The reference's own in-scope unit tests (kernels, Kronecker, mean functions, StVGP incl. the
+    optimisation against exact GP regression, GPMC incl. HMC) run, unmodified, over the TF / GPflow
+    stand-ins that produced the ref_*.npz fixtures."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-W", "ignore", "-m", "oracle.run_reference_tests"], cwd=root,
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.stdout.count("failures 0  errors 0") == 5, r.stdout
