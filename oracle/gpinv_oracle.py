@@ -33,7 +33,8 @@ GPflow 0.3 are not installable, but ``oracle/run_reference.py`` imports the unmo
 ``/root/reference/GPinv`` (and ``exec``s the notebook likelihood cells) over the torch-backed
 ``tensorflow`` / ``GPflow`` stand-ins in ``oracle/refshim`` and commits what it returns as
 ``tests/golden/ref_*.npz`` (ELBO / log-density, packed gradient, ``predict_f`` mean / variance /
-full covariance, LOS matrices; 10 model cases incl. BASELINE configs[0]).  This restatement
+full covariance, LOS matrices; 10 model cases incl. BASELINE configs[0], and compact fixtures
+``refc_*.npz`` for BASELINE configs[1] at full size n=1024, S=256 and an Abel case at n=512).  This restatement
 reproduces every one of them (``tests/test_oracle.py``: |df| <= 1e-9|f|, ||dg|| <= 1e-8||g||; measured
 <= 2e-11 and <= 1e-10).  The stand-ins themselves are validated by the reference's OWN unit tests:
 all 28 in-scope tests of ``testing/test_kernels.py``, ``test_kronecker.py``, ``test_mean.py``,

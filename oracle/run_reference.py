@@ -138,8 +138,29 @@ def compute_predict(name, index):
     return dict(x=out["x"], Xnew=Xnew, mu=mu, var=var, var_full=var_full)
 
 
+def compute_compact(name):
+    """Larger cases: run the reference, keep a compact summary (tests/golden/make_golden.py)."""
+    from tests.golden.make_golden import compact_case, compact_state, compact_summary
+    spec, S, hyper, q_mu, q_sqrt, eps = compact_case(name)
+    m = build_reference_model(spec, S)
+    m.kern.lengthscales = hyper["kern.lengthscales"]
+    m.kern.variance = hyper["kern.variance"]
+    m.likelihood.variance = hyper["likelihood.variance"]
+    if "mean_function.c" in hyper:
+        m.mean_function.c = hyper["mean_function.c"]
+    m.q_mu = q_mu
+    m.q_sqrt = q_sqrt
+    x = m.get_free_state()
+    n_hyper = x.size - q_mu.size - q_sqrt.size
+    assert np.array_equal(x, compact_state(x[:n_hyper], q_mu, q_sqrt))
+    f, g = m._objective(x, [eps[:, :, :, None]])
+    out = dict(x_hyper=x[:n_hyper].copy(), f=np.float64(f))
+    out.update(compact_summary(g, n_hyper))
+    return out
+
+
 def main():
-    from tests.golden.make_golden import REF_CASES
+    from tests.golden.make_golden import REF_CASES, COMPACT_CASES
     check = "--check" in sys.argv
     worst = 0.0
     for i, name in enumerate(REF_CASES):
@@ -165,6 +186,18 @@ def main():
         else:
             np.savez(path, **out)
             print("wrote %s" % os.path.basename(path))
+    for name in COMPACT_CASES:
+        out = compute_compact(name)
+        path = os.path.join(GOLDEN, "refc_%s.npz" % name)
+        if check:
+            d = np.load(path)
+            e = max(abs(float(d["f"]) - float(out["f"])) / abs(float(out["f"])),
+                    np.max(np.abs(d["g_proj"] - out["g_proj"]) / np.abs(out["g_proj"])))
+            worst = max(worst, e)
+            print("check %-32s f=%.15g  max rel diff vs committed fixture %.1e" % (name, out["f"], e))
+        else:
+            np.savez(path, **out)
+            print("wrote %-32s f=%.15g |g_rest|=%.6g" % (name, out["f"], out["g_rest_norm"]))
     # the reference's own LOS generator on the cfg1 grid (pins the vectorised product generator)
     r, z = np.linspace(0, 1., 30), np.linspace(-0.9, 0.9, 40)
     A, cosT = reference_los(r, z)

@@ -74,6 +74,56 @@ def build_spec(name):
     raise KeyError(name)
 
 
+# ---- larger cases with COMPACT fixtures (the state / gradient have 1e5..1e6 entries: the fixture
+# stores the hyper-parameter part of x, the value, and seeded projections / samples of the gradient;
+# the big blocks of x and the draws are regenerated from seeds on every side) ----
+COMPACT_CASES = ["cfg2_gauss_n1024", "abel_stvgp_n512"]
+
+
+def compact_case(name):
+    """(spec, S, hyper values, q_mu, q_sqrt, eps) of a compact case; BASELINE.json configs[1] for
+    cfg2 (lengthscale 0.5, variance 1, noise 0.09, q seeds 1, eps seed 2)."""
+    rng = np.random.RandomState(1)
+    if name == "cfg2_gauss_n1024":
+        n, S = 1024, 256
+        X = np.linspace(0, 6, n)[:, None]
+        Y = np.sin(X) + 0.3 * np.random.RandomState(0).randn(n, 1)
+        spec = dict(model="stvgp", X=X, Y=Y, kern=dict(type="rbf", input_dim=1, output_dim=1, ARD=False),
+                    mean=dict(type="zero", output_dim=1), lik=dict(type="gaussian"), num_latent=1)
+        hyper = {"kern.lengthscales": 0.5, "kern.variance": np.ones(1), "likelihood.variance": 0.09}
+    elif name == "abel_stvgp_n512":
+        n, S = 512, 32
+        r, z, A, y = _abel(n, 400)
+        spec = dict(model="stvgp", X=r[:, None], Y=y[:, None],
+                    kern=dict(type="rbf_csym", input_dim=1, output_dim=1, ARD=False),
+                    mean=dict(type="constant", output_dim=1), lik=dict(type="abel", A=A), num_latent=1)
+        hyper = {"kern.lengthscales": 0.3, "kern.variance": np.ones(1), "likelihood.variance": np.ones(1),
+                 "mean_function.c": np.zeros(1)}
+    else:
+        raise KeyError(name)
+    q_mu = 0.3 * rng.randn(n, 1)
+    q_sqrt = (0.5 * np.eye(n) + 0.05 / np.sqrt(n) * np.tril(rng.randn(n, n)))[:, :, None]
+    eps = np.random.RandomState(2).randn(1, S, n)
+    return spec, S, hyper, q_mu, q_sqrt, eps
+
+
+def compact_state(x_hyper, q_mu, q_sqrt):
+    """free state = [hyper-parameters (stored in the fixture), q_mu, q_sqrt] (identity transforms)."""
+    return np.concatenate([np.asarray(x_hyper, dtype=np.float64).ravel(), q_mu.ravel(), q_sqrt.ravel()])
+
+
+def compact_summary(g, n_hyper):
+    """What a compact fixture keeps of a gradient: hyper part, block norms, 8 seeded projections,
+    2000 seeded samples."""
+    g = np.asarray(g, dtype=np.float64)
+    rest = g[n_hyper:]
+    rng = np.random.RandomState(77)
+    idx = rng.randint(0, rest.size, size=2000)
+    proj = np.array([rest.dot(np.random.RandomState(100 + k).randn(rest.size)) for k in range(8)])
+    return dict(g_hyper=g[:n_hyper].copy(), g_rest_norm=np.float64(np.linalg.norm(rest)), g_proj=proj,
+                g_samples=rest[idx].copy())
+
+
 # cases whose fixtures are produced by the reference's own code (oracle/run_reference.py)
 REF_CASES = CASES + ["gauss_stvgp_full_klanalytic", "ard_multi_gauss", "rbf2d_kron_qdiag",
                      "abel_stvgp_cfg1", "abel_stvgp_n200"]

@@ -133,3 +133,18 @@ def same_evaluation(f1, g1, f0, g0, n_hyper, f_tol=1e-10, q_tol=1e-10, hyper_tol
         return False
     h1, h0 = g1[:n_hyper], g0[:n_hyper]
     return bool(np.all(np.abs(h1 - h0) <= hyper_tol * np.maximum(np.abs(h0), 1e-300)))
+
+
+def check_compact(f, g, d, n_hyper, f_tol, g_tol, hyper_tol):
+    """Compare a value / gradient with a compact reference-executed fixture (refc_*.npz): value,
+    norm / 8 seeded projections / 2000 seeded samples of the variational blocks, and each
+    hyper-parameter gradient (conditioning-aware bound)."""
+    from tests.golden.make_golden import compact_summary
+    s = compact_summary(g, n_hyper)
+    assert abs(f - float(d["f"])) <= f_tol * abs(float(d["f"])), (f, float(d["f"]))
+    scale = float(d["g_rest_norm"])
+    assert abs(float(s["g_rest_norm"]) - scale) <= g_tol * scale
+    # a projection on a unit-variance Gaussian direction has magnitude ~ |g|; bound the error by it
+    assert np.max(np.abs(s["g_proj"] - d["g_proj"])) <= g_tol * scale * 10
+    assert np.linalg.norm(s["g_samples"] - d["g_samples"]) <= g_tol * max(np.linalg.norm(d["g_samples"]), 1e-300) * 10
+    assert np.all(np.abs(s["g_hyper"] - d["g_hyper"]) <= hyper_tol * np.abs(d["g_hyper"])), (s["g_hyper"], d["g_hyper"])

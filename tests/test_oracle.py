@@ -219,3 +219,17 @@ def test_reference_own_unit_tests_pass_over_the_shim():
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert r.stdout.count("failures 0  errors 0") == 5, r.stdout
+
+
+@pytest.mark.parametrize("name", ["cfg2_gauss_n1024", "abel_stvgp_n512"])
+def test_oracle_matches_compact_reference_fixture(name):
+    """BASELINE.json configs[1] (n=1024, S=256) and a mid-size Abel case, computed by the reference's
+    own tile-and-batch-matmul code over the shim; the fixture keeps projections of the gradient."""
+    from tests.golden.make_golden import compact_case, compact_state
+    from tests.helpers import check_compact
+    d = np.load(os.path.join(GOLDEN, "refc_%s.npz" % name))
+    spec, S, hyper, q_mu, q_sqrt, eps = compact_case(name)
+    x = compact_state(d["x_hyper"], q_mu, q_sqrt)
+    assert O.state_size(spec) == x.size
+    f, g = O.objective(spec, x, eps)
+    check_compact(f, g, d, d["x_hyper"].size, f_tol=1e-9, g_tol=1e-8, hyper_tol=1e-5)

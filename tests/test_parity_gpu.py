@@ -220,6 +220,22 @@ def test_reference_executed_predict_fixtures(name):
     assert np.allclose(vf, d["var_full"], rtol=1e-7, atol=1e-9)
 
 
+@pytest.mark.parametrize("name", ["cfg2_gauss_n1024", "abel_stvgp_n512"])
+def test_compact_reference_executed_fixtures(name):
+    """CUDA path at BASELINE.json configs[1] size (n=1024, S=256, |x| = 1.05 M) and at a mid-size
+    Abel case against the reference's own code (compact fixture: value, hyper-gradients,
+    norm / projections / samples of the 1e5..1e6-entry variational gradient)."""
+    from tests.golden.make_golden import compact_case, compact_state
+    from tests.helpers import check_compact, model_from_spec
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "refc_%s.npz" % name))
+    spec, S, hyper, q_mu, q_sqrt, eps = compact_case(name)
+    m = model_from_spec(spec, S=S)
+    x = compact_state(d["x_hyper"], q_mu, q_sqrt)
+    assert m.get_free_state().size == x.size
+    f, g = m._objective(x, eps=eps)
+    check_compact(f, g, d, d["x_hyper"].size, f_tol=1e-8, g_tol=1e-8, hyper_tol=1e-5)
+
+
 def test_product_los_generator_matches_reference_fixture():
     from gpinv_b200.los import make_LosMatrix, make_cosTheta
     d = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_los_30x40.npz"))
