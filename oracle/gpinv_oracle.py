@@ -328,8 +328,16 @@ def lik_gaussian_logp(F, Y, var):
 
 
 def abel_transform(F, A):
-    """notebooks/Abel_inversion.ipynb:279-283: A . exp(F) per sample; F [S,n,1] -> [S,M,1]."""
-    return torch.matmul(A[None], torch.exp(F))
+    """notebooks/Abel_inversion.ipynb:279-283: A . exp(F) per sample; F [S,n,1] -> [S,M,1].
+    GEMM form exp(F)[S,n] @ A^T: the same sums as the notebook's tile-and-batch-matmul
+    (``abel_transform_literal``; tests assert they agree to 1e-12), but A is streamed once per
+    evaluation instead of once per sample -- the form the CPU baseline is timed in."""
+    return torch.matmul(torch.exp(F[:, :, 0]), A.T)[:, :, None]
+
+
+def abel_transform_literal(F, A):
+    """Literal form of the notebook cell: tf.tile(A) to [S,M,n], one mat-vec per sample."""
+    return torch.matmul(A[None].expand(F.shape[0], -1, -1), torch.exp(F))
 
 
 def lik_abel_logp(F, Y, A, var):

@@ -159,8 +159,47 @@ def compute_compact(name):
     return out
 
 
+def _assign(m, name, value):
+    """m.<dotted name> = value (list containers indexed by position)."""
+    obj = m
+    parts = name.split(".")
+    for p in parts[:-1]:
+        obj = obj[int(p)] if p.isdigit() else getattr(obj, p)
+    setattr(obj, parts[-1], value)
+
+
+def compute_baseline(name):
+    """A BASELINE.json configuration (tests/baseline_configs.py) through the reference's own code:
+    the model is built from the spec, the constrained values are assigned the way a user does
+    (``m.kern.lengthscales = 0.3``), and its free state must come out as the case's packed ``x``."""
+    from tests import baseline_configs as B
+    from oracle import gpinv_oracle as O
+    c = B.case(name, O.make_los_matrix, O.make_cos_theta)
+    m = build_reference_model(c["spec"], c["S"])
+    for k in c["order"]:
+        _assign(m, k, c["constrained"][k])
+    x = m.get_free_state()
+    assert x.size == c["x"].size and np.allclose(x, c["x"], rtol=1e-13, atol=1e-13), name
+    draws = [] if c["eps"] is None else [c["eps"][:, :, :, None]]
+    f, g = m._objective(c["x"], draws)
+    out = dict(f=np.float64(f), x_head=c["x"][:8].copy(), x_sum=np.float64(c["x"].sum()))
+    out.update(B.compact_summary(g, B.hyper_mask(c)))
+    return out
+
+
 def main():
-    from tests.golden.make_golden import REF_CASES, COMPACT_CASES
+    from tests.golden.make_golden import REF_CASES, COMPACT_CASES, REF_BASELINE
+    if "--baseline" in sys.argv:
+        # minutes of CPU and tens of GB of tiles: generated on demand, not part of --check
+        import time
+        names = [a for a in sys.argv[1:] if not a.startswith("--")] or REF_BASELINE
+        for name in names:
+            t0 = time.time()
+            out = compute_baseline(name)
+            np.savez(os.path.join(GOLDEN, "refb_%s.npz" % name), **out)
+            print("wrote refb_%-18s f=%.15g |g_rest|=%.6g  (%.1f s)" % (name, out["f"], out["g_rest_norm"], time.time() - t0),
+                  flush=True)
+        return
     check = "--check" in sys.argv
     worst = 0.0
     for i, name in enumerate(REF_CASES):
