@@ -19,18 +19,21 @@ def conditional(Xnew, X, kern, f, full_cov=False, q_sqrt=None, whiten=False):
         chol = type(chol)([torch.kron(c[0], c[1]) for c in chol.cores], chol.sqrt_var,
                           chol.core_index, chol.infos, False)
     R = chol.num_latent
-    variance = torch.square(chol.sqrt_var)
+    # A_r = Lm_r^{-1} Kmn_r with Lm_r = sqrt_var_r * core factor and Kmn_r = variance_r * core(X, Xnew):
+    # the scalar is variance_r / sqrt_var_r (= sqrt(variance_r) for the built-in factored kernels;
+    # a kernel that overrides Cholesky() hands over unit-variance cores that already carry it)
+    kvar = torch.cat([k.variance.reshape(-1) for k in _core_kernels(kern)])
     Kdiag = kern.Kdiag(Xnew)                                     # [n2,R]
     Knn = kern.K(Xnew) if full_cov else None                     # [n2,n2,R]
     means, vars_ = [None] * R, [None] * R
-    subkerns = _core_kernels(kern)
-    for gi, (core, r0, r1) in enumerate(chol.groups()):
-        k = subkerns[gi]
+    out_kern = [k for k in _core_kernels(kern) for _ in range(k.output_dim)]   # output r -> its kernel
+    for core, r0, r1 in chol.groups():
+        k = out_kern[r0]
         Knm = k._Kcore(Xnew, X)                                  # [n2,n] core(Xnew, X)
         AT = ops.trsm_rlt(core, Knm)                             # [n2,n] = (Lc^{-1} core_mn)^T
         for r in range(r0, r1):
-            sv = chol.sqrt_var[r]
-            ATr = AT * sv                                        # A_r^T = sqrt(v) Lc^{-1} core_mn
+            sv = kvar[r] / chol.sqrt_var[r]
+            ATr = AT * sv                                        # A_r^T = (v_r / sqrt_var_r) Lc^{-1} core_mn
             fmean = ops.gemm(ATr.contiguous(), f[:, r:r + 1].contiguous(), False, False, False)[:, 0]
             if full_cov:
                 fvar = Knn[:, :, r] - ops.gemm(ATr.contiguous(), ATr.contiguous(), False, True, False)

@@ -96,3 +96,13 @@ inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 namespace gpinv {
 void set_last_error(const char* msg);
 }
+
+// Run a CUDA runtime call; on failure record its error string and return GPINV_ERR_CUDA.
+#define GPINV_TRY(call)                                       \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) {                                 \
+      gpinv::set_last_error(cudaGetErrorString(e__));         \
+      return GPINV_ERR_CUDA;                                  \
+    }                                                         \
+  } while (0)

@@ -212,7 +212,7 @@ int kbuild_bwd_ex_f64(const double* X, const double* X2, int n, int n2, int D, i
     n2 = n;
   }
   const int nls = ard ? D : 1;
-  if (cudaMemsetAsync(ls_bar, 0, nls * sizeof(double), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaMemsetAsync(ls_bar, 0, nls * sizeof(double), st));
   dim3 grid(cdiv(n2, 128), cdiv(n, 16));
   for (int l = 0; l < nls; ++l) {
     const int dsel = ard ? l : -1;

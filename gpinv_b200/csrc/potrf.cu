@@ -440,7 +440,7 @@ int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaSt
   using namespace pcfg;
   int rc = set_smem_attrs();
   if (rc) return rc;
-  if (cudaMemsetAsync(info, 0, 2 * sizeof(int), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaMemsetAsync(info, 0, 2 * sizeof(int), st));
   static const bool no_la = (getenv("GPINV_NO_LOOKAHEAD") != nullptr);
   LookAhead* la = (n > 2 * NBO && !no_la) ? lookahead_for_current_device() : nullptr;
   bool side_pending = false;
@@ -469,9 +469,9 @@ int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaSt
     }
     const int nw = min(NBO, n - t0);   // width of the next outer panel
     const int t1 = t0 + nw;
-    if (cudaEventRecord(la->evP, st) != cudaSuccess) return GPINV_ERR_CUDA;
-    if (cudaStreamWaitEvent(la->side, la->evP, 0) != cudaSuccess) return GPINV_ERR_CUDA;
-    if (side_pending && cudaStreamWaitEvent(st, la->evB, 0) != cudaSuccess) return GPINV_ERR_CUDA;
+    GPINV_TRY(cudaEventRecord(la->evP, st));
+    GPINV_TRY(cudaStreamWaitEvent(la->side, la->evP, 0));
+    if (side_pending) GPINV_TRY(cudaStreamWaitEvent(st, la->evB, 0));
     // (a) next panel's columns, all trailing rows (the upper part of its diagonal block is junk)
     rc = gemm_simple(LK, LK, n - t0, nw, w, -1.0, P, lda, P, lda, 1.0, A + (size_t)t0 * lda + t0,
                      lda, false, 0, 1, st);
@@ -496,11 +496,11 @@ int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaSt
       gp.force_cfg = cap > 0 ? 1 : 0;
       rc = gemm_launch(LK, LK, EF_BETA | EF_LOWER, gp, la->side);
       if (rc) return rc;
-      if (cudaEventRecord(la->evB, la->side) != cudaSuccess) return GPINV_ERR_CUDA;
+      GPINV_TRY(cudaEventRecord(la->evB, la->side));
       side_pending = true;
     }
   }
-  if (side_pending && cudaStreamWaitEvent(st, la->evB, 0) != cudaSuccess) return GPINV_ERR_CUDA;
+  if (side_pending) GPINV_TRY(cudaStreamWaitEvent(st, la->evB, 0));
   dim3 blk(32, 8);
   if (upper_is_zero) {
     dim3 grd(cdiv(NBO, 32), cdiv(NBO, 8), cdiv(n, NBO));
@@ -735,9 +735,8 @@ static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cuda
   static bool attr = false;
   const int smem = (NB * LDT + NB + NB * LDR) * 8;
   if (!attr) {
-    if (cudaFuncSetAttribute(trtri_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem) != cudaSuccess)
-      return GPINV_ERR_CUDA;
+    GPINV_TRY(cudaFuncSetAttribute(trtri_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem));
     attr = true;
   }
   trtri_leaf_kernel<<<cdiv(n, NB), NB, smem, st>>>(L, ldl, W, n, n);
@@ -778,7 +777,7 @@ int potrf_bwd_inv_f64(const double* L, int ldl, double* Ab, int ldab, int n, dou
   double* W = ws;
   double* P = W + (size_t)n * n;
   double* T1 = P + (size_t)n * n;
-  if (cudaMemsetAsync(W, 0, (size_t)n * n * sizeof(double), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaMemsetAsync(W, 0, (size_t)n * n * sizeof(double), st));
   int rc = trtri_f64(L, ldl, W, P, n, st);
   if (rc) return rc;
   dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n, 8));
@@ -867,7 +866,7 @@ int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int 
   double* W = ws;                       // n x n, only the m x m diagonal blocks are non-zero
   double* S1 = W + (size_t)n * n;       // scratch: Cbar W_bb  /  P
   double* S2 = S1 + (size_t)n * n;      // scratch: T1  /  symmetrised block
-  if (cudaMemsetAsync(W, 0, (size_t)n * n * sizeof(double), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaMemsetAsync(W, 0, (size_t)n * n * sizeof(double), st));
   int rc = trtri_f64(L, ldl, W, S1, n, st, m);
   if (rc) return rc;
   dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n, 8));
@@ -886,19 +885,32 @@ int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int 
     double* Dbar = Ab + (size_t)s * ldab + s;
     double* Cb = Ab + (size_t)e * ldab + s;            // rows below the block
     if (r > 0) {
-      // Cbar <- Cbar W_bb   (W_bb lower: B(c,k) = W[k][c] vanishes for k < c)
+      // Cbar <- Cbar D^{-1} by the explicit block inverse PLUS one step of iterative refinement:
+      //   X0 = Cbar W_bb,   R = Cbar - X0 D,   X1 = X0 + R W_bb      (W_bb, D lower: k >= column)
+      // Multiplying by an explicit inverse is not backward stable (residual ~ cond(D) eps), and the
+      // lengthscale gradient -- a sum over Kbar that cancels to ~1e-6 of its terms -- sees it: against
+      // the longdouble arbiter (oracle/arbiter.py) the unrefined sweep was off by 7.6e-6 at n = 2048
+      // where the substitution-based sweep and the refined one are at ~1e-8.  Costs two more
+      // r x m x m triangular GEMMs per block column; the copy-back of X disappears into the last one.
       rc = gemm_ws(LK, LMN, EF_BETA, r, bw, bw, 1.0, Cb, ldab, Wbb, n, 0.0, nullptr, 0, S1, bw, 2, st);
       if (rc) return rc;
-      if (cudaMemcpy2DAsync(Cb, (size_t)ldab * sizeof(double), S1, (size_t)bw * sizeof(double),
-                            (size_t)bw * sizeof(double), r, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-        return GPINV_ERR_CUDA;
+      static const bool no_refine = (getenv("GPINV_BWD_NO_REFINE") != nullptr);
+      if (no_refine) {
+        GPINV_TRY(cudaMemcpy2DAsync(Cb, (size_t)ldab * sizeof(double), S1, (size_t)bw * sizeof(double),
+                                    (size_t)bw * sizeof(double), r, cudaMemcpyDeviceToDevice, st));
+      } else {
+        rc = gemm_ws(LK, LMN, EF_BETA, r, bw, bw, -1.0, S1, bw, Lbb, ldl, 1.0, Cb, ldab, S2, bw, 2, st);
+        if (rc) return rc;
+        rc = gemm_ws(LK, LMN, EF_BETA, r, bw, bw, 1.0, S2, bw, Wbb, n, 1.0, S1, bw, Cb, ldab, 2, st);
+        if (rc) return rc;
+      }
       // Two independent chains follow from Cbar: {Bbar -= Cbar R, Rbar -= Cbar^T B} (big GEMMs) and
       // {Dbar -= tril(Cbar^T C), diagonal-block reverse} (small, latency-bound GEMMs).  The first
       // runs on the side stream (second half of the split-K workspace) beside the second.
       forked = false;
       if (s > 0 && la2) {
-        if (cudaEventRecord(la2->evP, st) != cudaSuccess) return GPINV_ERR_CUDA;
-        if (cudaStreamWaitEvent(la2->side, la2->evP, 0) != cudaSuccess) return GPINV_ERR_CUDA;
+        GPINV_TRY(cudaEventRecord(la2->evP, st));
+        GPINV_TRY(cudaStreamWaitEvent(la2->side, la2->evP, 0));
         forked = true;
       }
       if (s > 0) {
@@ -913,7 +925,7 @@ int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int 
         rc = gemm_ws(LMN, LMN, EF_BETA, bw, s, r, -1.0, Cb, ldab, L + (size_t)e * ldl, ldl, 1.0, Rb2, ldab,
                      Rb2, ldab, 0, s2, slot);
         if (rc) return rc;
-        if (forked && cudaEventRecord(la2->evB, la2->side) != cudaSuccess) return GPINV_ERR_CUDA;
+        if (forked) GPINV_TRY(cudaEventRecord(la2->evB, la2->side));
       }
       // Dbar -= tril(Cbar^T C)
       rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, r, -1.0, Cb, ldab, L + (size_t)e * ldl + s, ldl,
@@ -943,7 +955,7 @@ int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int 
     }
     if (s > 0) {
       double* Rb = Ab + (size_t)s * ldab;               // Rbar: block rows, columns [0, s)
-      if (forked && cudaStreamWaitEvent(st, la2->evB, 0) != cudaSuccess) return GPINV_ERR_CUDA;
+      if (forked) GPINV_TRY(cudaStreamWaitEvent(st, la2->evB, 0));
       forked = false;
       // Rbar -= (Dbar + Dbar^T) R
       dim3 g2(cdiv(bw, 32), cdiv(bw, 8));
@@ -1044,9 +1056,8 @@ int trsm_rlt_f64(const double* L, int ldl, double* X, int ldx, int m, int n, cud
   using namespace pcfg;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(trsm_rlt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             TRSM_SMEM) != cudaSuccess)
-      return GPINV_ERR_CUDA;
+    GPINV_TRY(cudaFuncSetAttribute(trsm_rlt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TRSM_SMEM));
     attr = true;
   }
   if (m <= 0) return GPINV_OK;

@@ -197,7 +197,7 @@ int tril_pack_f64(const double* src, double* dst, int n, int R, cudaStream_t st)
 }
 
 int sumsq_f64(const double* x, size_t count, double* out, cudaStream_t st) {
-  if (cudaMemsetAsync(out, 0, sizeof(double), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaMemsetAsync(out, 0, sizeof(double), st));
   sumsq_kernel<<<ew_grid(count / 2 + 1), 256, 0, st>>>(x, count, out);
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
@@ -209,7 +209,7 @@ int sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
                    double* U, double* F, double* expF, double* kl_out, cudaStream_t st) {
   if (n <= 0 || S <= 0 || R <= 0) return GPINV_ERR_ARG;
   if (!F && !expF) return GPINV_ERR_ARG;
-  if (cudaMemsetAsync(kl_out, 0, 4 * sizeof(double), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaMemsetAsync(kl_out, 0, 4 * sizeof(double), st));
   const size_t sn = (size_t)S * n;
   sumsq_kernel<<<ew_grid((size_t)R * sn / 2 + 1), 256, 0, st>>>(E, (size_t)R * sn, kl_out + 1);
   GPINV_CHECK_LAUNCH();
@@ -263,12 +263,10 @@ int sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
                    double* Lc_bar, int ldlb, double* svdot, double* mean_bar, cudaStream_t st) {
   if (n <= 0 || S <= 0 || R <= 0) return GPINV_ERR_ARG;
   const size_t sn = (size_t)S * n;
-  if (cudaMemsetAsync(qmu_bar, 0, (size_t)R * n * sizeof(double), st) != cudaSuccess ||
-      cudaMemsetAsync(mean_bar, 0, (size_t)R * n * sizeof(double), st) != cudaSuccess ||
-      cudaMemsetAsync(svdot, 0, (size_t)R * sizeof(double), st) != cudaSuccess)
-    return GPINV_ERR_CUDA;
-  if (q_diag && cudaMemsetAsync(Qbar, 0, (size_t)R * n * sizeof(double), st) != cudaSuccess)
-    return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaMemsetAsync(qmu_bar, 0, (size_t)R * n * sizeof(double), st));
+  GPINV_TRY(cudaMemsetAsync(mean_bar, 0, (size_t)R * n * sizeof(double), st));
+  GPINV_TRY(cudaMemsetAsync(svdot, 0, (size_t)R * sizeof(double), st));
+  if (q_diag) GPINV_TRY(cudaMemsetAsync(Qbar, 0, (size_t)R * n * sizeof(double), st));
   const int schunk = 64;
   {
     dim3 grid(cdiv(n, 256), cdiv(S, schunk), R);
@@ -332,7 +330,7 @@ int sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
 
 int gauss_sumsq_f64(const double* F, const double* Y, int n, int S, int R, double* out,
                     cudaStream_t st) {
-  if (cudaMemsetAsync(out, 0, sizeof(double), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaMemsetAsync(out, 0, sizeof(double), st));
   gauss_sumsq_kernel<<<ew_grid((size_t)R * S * n), 256, 0, st>>>(F, Y, n, S, R, out);
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
@@ -348,7 +346,7 @@ int gauss_bwd_f64(const double* F, const double* Y, int n, int S, int R, const d
 // Rs[S,M] = 1 y^T - expF[S,n] A[M,n]^T ; *sumsq = sum Rs^2
 int abel_fwd_f64(const double* expF, const double* A, int lda, const double* Y, int n, int M, int S,
                  double* Rs, double* sumsq, cudaStream_t st) {
-  if (cudaMemsetAsync(sumsq, 0, sizeof(double), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaMemsetAsync(sumsq, 0, sizeof(double), st));
   GemmParams p = {};
   p.A = expF; p.lda = n;
   p.B = A; p.ldb = lda;

@@ -105,7 +105,7 @@ int spec_fwd_f64(const double* F, const double* A, const double* cosT, const dou
                  const double* Y, int n, int m, int k, int S, double* P, double* sumsq,
                  cudaStream_t st) {
   if (n <= 0 || n > SPEC_MAX_N || m <= 0 || k <= 0 || S <= 0) return GPINV_ERR_ARG;
-  if (sumsq && cudaMemsetAsync(sumsq, 0, sizeof(double), st) != cudaSuccess) return GPINV_ERR_CUDA;
+  if (sumsq) GPINV_TRY(cudaMemsetAsync(sumsq, 0, sizeof(double), st));
   dim3 grid(cdiv(k * m, 256), S);
   spec_fwd_kernel<<<grid, 256, 3 * n * sizeof(double), st>>>(F, A, cosT, lam, Y, n, m, k, S, P, sumsq);
   GPINV_CHECK_LAUNCH();

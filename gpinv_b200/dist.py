@@ -44,6 +44,11 @@ class DistContext(object):
 
 def attach(model, ctx=None):
     """Make ``model._objective`` evaluate its shard and all-reduce [-f, -grad]."""
+    if not hasattr(model, "_eps_tensor"):
+        # GPMC evaluates the whole likelihood on every rank (S = 1, nothing to shard): summing the
+        # ranks would return G x the log-likelihood.  SURVEY.md 8(e): replicas only.
+        raise TypeError("%s has no Monte-Carlo samples to shard: run independent replicas (one chain "
+                        "per GPU) instead of dist.attach()" % type(model).__name__)
     model.dist = ctx if ctx is not None else DistContext()
     return model
 

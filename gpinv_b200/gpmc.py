@@ -40,9 +40,15 @@ class GPMC(GPModel):
         """GPinv/gpmc.py:53-60 (the current state is one posterior sample)."""
         return self._run(lambda: self.likelihood.sample_F(self._get_f()[0]))
 
-    def sample_Y(self, n_sample=1):
-        """GPinv/gpmc.py:62-69."""
-        return self._run(lambda: self.likelihood.sample_Y(self._get_f()[0]))
+    def sample_Y(self, n_sample=1, noise=None):
+        """GPinv/gpmc.py:62-69 (``noise`` fixes the observation-noise draws)."""
+        def fn():
+            f = self._get_f()[0]
+            if noise is None:
+                return self.likelihood.sample_Y(f)
+            nz = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float64)).to(f.device)
+            return self.likelihood.sample_Y(f, noise=nz)
+        return self._run(fn)
 
     def _get_f(self):
         """f = L V + mean, as a [1,n,R] sample set (GPinv/gpmc.py:71-82).  Reuses the sampling op

@@ -88,11 +88,25 @@ class Kern(Parameterized):
         return self.Cholesky_factor(X).dense()
 
     def Cholesky_factor(self, X):
-        core = self._Kcore(X, None, jitter=settings.numerics.jitter_level)
-        chol, info = ops.potrf(core)
+        """Factored ``Cholesky(X)`` for any kernel written against the reference's plugin
+        interface: ``_Kcore(self, X, X2=None)`` (GPinv/kernels.py:31-40) gives the core, the
+        jitter goes on the core before the variance scaling (GPinv/kernels.py:57-58), and the
+        factorisation / its reverse are the sm_100a ``potrf`` ops.  A subclass that overrides
+        ``Cholesky`` itself (as the reference's RBF2D does, GPinv/kronecker.py:49-66) is
+        honoured: its dense [n,n,R] tile becomes R unit-variance cores."""
+        if type(self).Cholesky is not Kern.Cholesky:
+            dense = type(self).Cholesky(self, X)                   # [n,n,R], user-defined
+            R = dense.shape[2]
+            cores = [dense[:, :, r].contiguous() for r in range(R)]
+            ones = torch.ones(R, dtype=dense.dtype, device=dense.device)
+            return CholeskyFactor(cores, ones, list(range(R)), [])
+        core = self._Kcore(X, None)
+        n = core.shape[0]
+        core = core + settings.numerics.jitter_level * torch.eye(n, dtype=core.dtype, device=core.device)
+        chol, info = ops.potrf(core.contiguous())
         return CholeskyFactor([chol], torch.sqrt(self.variance), [0] * self.output_dim, [info])
 
-    def _Kcore(self, X, X2=None, jitter=0.0):
+    def _Kcore(self, X, X2=None):
         raise NotImplementedError
 
 

@@ -37,7 +37,7 @@ class Likelihood(Parameterized):
     def sample_F(self, F):
         raise NotImplementedError("implement the sample_F function for this likelihood")
 
-    def sample_Y(self, F):
+    def sample_Y(self, F, noise=None):
         raise NotImplementedError("implement the sample_Y function for this likelihood")
 
 
@@ -65,8 +65,9 @@ class Gaussian(Likelihood):
     def sample_F(self, F):
         return F
 
-    def sample_Y(self, F):
-        return F + torch.sqrt(self.variance) * torch.randn_like(F)
+    def sample_Y(self, F, noise=None):
+        """GPinv/likelihoods.py:78-82: F + sqrt(variance) * N(0,1) (``noise`` fixes the draws)."""
+        return F + torch.sqrt(self.variance) * (torch.randn_like(F) if noise is None else noise)
 
 
 class AbelLikelihood(Likelihood):
@@ -96,9 +97,9 @@ class AbelLikelihood(Likelihood):
         X = torch.exp(F[:, :, 0]).contiguous()               # [S,n]
         return ops.gemm(X, self.Amat, False, True, False)[:, :, None]   # [S,M,1]
 
-    def sample_Y(self, F):
+    def sample_Y(self, F, noise=None):
         f = self.sample_F(F)
-        return f + torch.randn_like(f) * torch.sqrt(self.variance)
+        return f + (torch.randn_like(f) if noise is None else noise) * torch.sqrt(self.variance)
 
 
 class SpecAbelLikelihood(Likelihood):
@@ -136,6 +137,6 @@ class SpecAbelLikelihood(Likelihood):
         var = self.variance
         return -0.5 * float(P.numel()) * (LOG2PI + torch.log(var)) - 0.5 * ss / var
 
-    def sample_Y(self, F):
+    def sample_Y(self, F, noise=None):
         f = self.sample_F(F)
-        return f + torch.randn_like(f) * torch.sqrt(self.variance)
+        return f + (torch.randn_like(f) if noise is None else noise) * torch.sqrt(self.variance)

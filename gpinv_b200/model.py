@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import hmc
-from .param import Parameterized, default_device
+from .param import Parameterized, default_device, state_epoch
 
 
 class OptimizeResult(dict):
@@ -78,6 +78,11 @@ class Model(Parameterized):
         self._prepare()
         dyn = self._graph_inputs(kw)
         key = (x.numel(),) + tuple((k, tuple(v.shape)) for k, v in sorted(dyn.items()))
+        if getattr(self, "_graph_epoch", None) != state_epoch():
+            # data, a fixed value, the jitter level ... changed on the host since the capture: the
+            # graph may have baked the old value (or a freed address) in.  Re-capture.
+            self._graphs = {}
+            self._graph_epoch = state_epoch()
         ent = self._graphs.get(key)
         if ent is None:
             sx = x.detach().clone()
@@ -94,11 +99,28 @@ class Model(Parameterized):
             cur.wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                f, g = self._objective_eager(sx, reduce=False, **sdyn)
-            ent = (graph, sx, sdyn, f, g, list(self._pending_infos))
+            # Nothing but this evaluation may touch CUDA while the capture is open: a garbage
+            # collection that frees device or pinned memory of unrelated objects in the middle of
+            # it invalidates the capture (seen when an earlier test had failed and its frames were
+            # still alive), so collect now and keep the collector off until the capture ends; calls
+            # of other threads (pinned-allocator event queries ...) are not checked (thread_local).
+            import gc
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    f, g = self._objective_eager(sx, reduce=False, **sdyn)
+            finally:
+                if gc_was_on:
+                    gc.enable()
+            # strong references to every non-input tensor the capture read (data holders, fixed
+            # Params): the caching allocator must not hand their memory out while the graph lives
+            keep = [d._tensor for nd in self._all_parameterized() for d in nd.data_holders] + \
+                   [p._fixed_dev for p in self.all_params() if p.fixed]
+            ent = (graph, sx, sdyn, f, g, list(self._pending_infos), keep)
             self._graphs[key] = ent
-        graph, sx, sdyn, f, g, infos = ent
+        graph, sx, sdyn, f, g, infos, _keep = ent
         sx.copy_(x)
         for k, v in dyn.items():
             sdyn[k].copy_(v)

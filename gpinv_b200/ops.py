@@ -38,6 +38,26 @@ def _chk(t: Tensor, name: str) -> Tensor:
 
 _SPLIT_WS = {}
 
+# bench.py sets this to a dict to time single ops inside an eager evaluation: name -> [(start, end)]
+# CUDA events recorded on the launching stream.  None (default): no events are recorded.
+TIMERS = None
+
+
+class _timed(object):
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMERS is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+
+    def __exit__(self, *exc):
+        if TIMERS is not None:
+            self.ev[1].record()
+            TIMERS.setdefault(self.name, []).append(self.ev)
+        return False
+
 
 def ensure_workspace(device, nbytes: int = 320 << 20):
     """Register the (zero-initialised, persistent) split-K workspace for `device` once."""
@@ -395,7 +415,8 @@ def abel_resid(F: Tensor, expF: Tensor, A: Tensor, Y: Tensor) -> Tuple[Tensor, T
     M = A.shape[0]
     Rs = torch.empty((S, M), dtype=torch.float64, device=expF.device)
     ss = torch.empty(1, dtype=torch.float64, device=expF.device)
-    rc = _capi.lib().gpinv_abel_fwd_f64(_p(expF), _p(A), n, _p(Y), n, M, S, _p(Rs), _p(ss), _st())
+    with _timed("abel_resid"):
+        rc = _capi.lib().gpinv_abel_fwd_f64(_p(expF), _p(A), n, _p(Y), n, M, S, _p(Rs), _p(ss), _st())
     _capi.check(rc, "abel_fwd")
     return ss, Rs
 

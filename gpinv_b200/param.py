@@ -27,6 +27,15 @@ from . import transforms
 
 _DEVICE = None
 
+# Bumped whenever something a captured CUDA graph may have baked in changes from the host side:
+# a DataHolder gets new data, a Param is assigned a value, a Param is fixed / released.  Model
+# compares it with the value recorded at capture time and re-captures (gpinv_b200/model.py).
+_STATE_EPOCH = [0]
+
+
+def state_epoch() -> int:
+    return _STATE_EPOCH[0]
+
 
 def default_device() -> torch.device:
     """The device model tensors live on.  CUDA only: there is no CPU compute path."""
@@ -72,7 +81,8 @@ class Param(Parentable):
     def __init__(self, array, transform=None):
         self._array = np.array(np.atleast_1d(array), dtype=np.float64)
         self.transform = transform if transform is not None else transforms.Identity()
-        self.fixed = False
+        self._fixed = False
+        self._fixed_dev = None      # device copy of a fixed Param (uploaded outside graph capture)
         self.prior = None
         self._tensor = None
         self._free_leaf = None
@@ -82,6 +92,27 @@ class Param(Parentable):
     @property
     def value(self):
         return self._array.copy()
+
+    @property
+    def fixed(self):
+        return self._fixed
+
+    @fixed.setter
+    def fixed(self, flag):
+        if bool(flag) != self._fixed:
+            self._fixed = bool(flag)
+            self._fixed_dev = None
+            _STATE_EPOCH[0] += 1
+
+    def fixed_tensor(self, device):
+        """Device tensor of a fixed Param; uploaded once (and again after ``assign``), never
+        inside a CUDA-graph capture (a pageable host-to-device copy is illegal there)."""
+        if self._fixed_dev is None or self._fixed_dev.device != torch.device(device):
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("fixed Param %s has no device copy yet and a CUDA graph is being captured"
+                                   % self.long_name)
+            self._fixed_dev = torch.as_tensor(self._array, dtype=torch.float64).to(device)
+        return self._fixed_dev
 
     @property
     def shape(self):
@@ -110,6 +141,8 @@ class Param(Parentable):
         v = np.asarray(value, dtype=np.float64)
         self._array[...] = v
         self._tensor = None
+        self._fixed_dev = None
+        _STATE_EPOCH[0] += 1
 
     def __str__(self):
         return "%s transform:%s prior:%s%s\n%s" % (self.long_name, self.transform, self.prior,
@@ -138,8 +171,16 @@ class DataHolder(Parentable):
         array = np.ascontiguousarray(array, dtype=np.float64)
         if array.shape != self._array.shape and self.on_shape_change == "raise":
             raise ValueError("The shape of this data must not change (%s -> %s)" % (self._array.shape, array.shape))
-        self._array = array
-        self._tensor = None
+        if (self._tensor is not None and array.shape == self._array.shape
+                and not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing())):
+            # same shape: refresh the existing device tensor IN PLACE so that anything holding its
+            # address (a captured CUDA graph) reads the new data
+            self._array = array
+            self._tensor.copy_(torch.as_tensor(array, dtype=torch.float64))
+        else:
+            self._array = array
+            self._tensor = None
+            _STATE_EPOCH[0] += 1
 
     def tensor(self):
         if self._tensor is None:
@@ -259,7 +300,7 @@ class Parameterized(Parentable):
         off = 0
         for p in self.all_params():
             if p.fixed:
-                p._tensor = torch.as_tensor(p._array, dtype=torch.float64).to(x.device)
+                p._tensor = p.fixed_tensor(x.device)
                 p._free_leaf = None
                 continue
             n = p.size

@@ -108,18 +108,23 @@ class StVGP(GPModel):
                                            q_sqrt=self.q_sqrt, full_cov=full_cov, whiten=True)
         return mu + self.mean_function(Xnew), var
 
-    def sample_F(self, n_sample):
-        """Samples of the transformed latent function, [n_sample, ...] (GPinv/stvgp.py:124-132)."""
+    def sample_F(self, n_sample, eps=None):
+        """Samples of the transformed latent function, [n_sample, ...] (GPinv/stvgp.py:124-132).
+        ``eps`` [R,n_sample,n] fixes the draws (extension, like ``_objective(x, eps=)``)."""
         def fn():
-            f, _ = self._sample(self._eps_tensor(None, int(n_sample)))
+            f, _ = self._sample(self._eps_tensor(eps, int(n_sample)))
             return self.likelihood.sample_F(f)
         return self._run(fn)
 
-    def sample_Y(self, n_sample):
-        """GPinv/stvgp.py:134-142."""
+    def sample_Y(self, n_sample, eps=None, noise=None):
+        """GPinv/stvgp.py:134-142.  ``noise`` (shape of the result) fixes the observation-noise
+        draws of ``Likelihood.sample_Y`` (GPinv/likelihoods.py:78-82)."""
         def fn():
-            f, _ = self._sample(self._eps_tensor(None, int(n_sample)))
-            return self.likelihood.sample_Y(f)
+            f, _ = self._sample(self._eps_tensor(eps, int(n_sample)))
+            if noise is None:
+                return self.likelihood.sample_Y(f)
+            nz = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float64)).to(default_device())
+            return self.likelihood.sample_Y(f, noise=nz)
         return self._run(fn)
 
     def _sample(self, eps):

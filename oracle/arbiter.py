@@ -216,6 +216,43 @@ def arb_case(name):
     return case, spec, x, eps, nh
 
 
+def baseline_case(name):
+    """Arbiter inputs of a full-size BASELINE.json configuration with ONE latent function and an
+    RBF-family kernel: cfg2 (Gaussian regression), cfg4 (GPMC: u = V, no draws), cfg5 (headline)."""
+    from tests import baseline_configs as B
+    from oracle import gpinv_oracle as O
+    c = B.case(name, O.make_los_matrix, O.make_cos_theta)
+    spec, con = c["spec"], c["constrained"]
+    n = spec["X"].shape[0]
+    if spec["model"] == "gpmc":
+        q_mu, q_sqrt, eps = con["V"][:, 0], np.eye(n), np.zeros((1, n))
+    else:
+        q_mu, q_sqrt, eps = con["q_mu"][:, 0], con["q_sqrt"][:, :, 0], c["eps"][0]
+    has_mean = "mean_function.c" in con
+    case = dict(kind=spec["kern"]["type"], X=spec["X"], Y=spec["Y"], lik=spec["lik"]["type"],
+                A=spec["lik"].get("A"), has_mean=has_mean, q_mu=q_mu, q_sqrt=q_sqrt, eps=eps)
+    keys = ["kern.lengthscales", "kern.variance", "likelihood.variance"] + (["mean_function.c"] if has_mean else [])
+    pos = {"kern.lengthscales", "kern.variance", "likelihood.variance"}
+    xh = np.concatenate([np.log(np.expm1(np.asarray(con[k], dtype=np.float64).ravel() - 1e-6)) if k in pos
+                         else np.asarray(con[k], dtype=np.float64).ravel() for k in keys])
+    return case, xh, c
+
+
+def baseline_main(name):
+    """arb_<cfg>.npz: longdouble forward-mode lengthscale gradient (and the value) of a full-size
+    BASELINE configuration.  cfg5 takes ~25 minutes of one core (no BLAS for longdouble)."""
+    import time
+    t0 = time.time()
+    case, xh, c = baseline_case(name)
+    g_ls = lengthscale_gradient_analytic(case, xh)
+    f = -elbo(case, xh)
+    if c["spec"]["model"] == "gpmc":          # ELBO(q = delta at V) differs from the log joint by the prior's constant
+        f = f + LD(case["X"].shape[0]) * LD(0.5) * LOG2PI
+    np.savez(os.path.join(GOLDEN, "arb_%s.npz" % name), f=np.float64(f), g_ls=np.float64(g_ls),
+             f_hi=np.array([repr(f)]), g_hi=np.array([repr(g_ls)]), x_hyper=xh)
+    print("wrote arb_%s f=%s dls=%s (%.0f s)" % (name, repr(f), repr(g_ls), time.time() - t0), flush=True)
+
+
 ARB_CASES = ["gauss_n256", "gauss_n512", "gauss_n1024", "abel_n256", "abel_n512", "abel_n1024"]
 
 
@@ -232,6 +269,9 @@ def main():
                                                         np.abs(go[:nh] - g1.astype(np.float64)) / np.abs(g1.astype(np.float64))))
         return
     names = [a for a in sys.argv[1:] if not a.startswith("--")] or ARB_CASES
+    for name in [a for a in names if a.startswith("cfg")]:
+        baseline_main(name)
+    names = [a for a in names if not a.startswith("cfg")]
     for name in names:
         t0 = time.time()
         case, spec, x, eps, nh = arb_case(name)

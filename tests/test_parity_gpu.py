@@ -177,7 +177,7 @@ def test_golden_fixtures():
         mean_functions.Stack([mean_functions.Constant(2), mean_functions.Zero(1)]), num_latent=3)
     for f in sorted(glob.glob(os.path.join(here, "*.npz"))):
         name = os.path.splitext(os.path.basename(f))[0]
-        if name.startswith(("ref_", "refc_")):
+        if name.startswith(("ref_", "refc_", "refb_", "oc_", "arb_")):
             continue                      # reference-executed fixtures: tested below
         d = np.load(f)
         m = built[name]
@@ -353,16 +353,49 @@ def _baseline_model(c):
     return m
 
 
-# per-entry bound on the scalar hyper-gradients: what oracle/arbiter.py (longdouble) measured for
-# the torch-CPU oracle itself at cond(K) 1e8..2e9 (tests/test_oracle.py::test_oracle_against_arbiter)
-HYPER_TOL = 1e-6
+# Scalar hyper-gradients.  The lengthscale gradient cancels through cond(K) ~ 1e8..2e9, and the
+# np.longdouble arbiter (oracle/arbiter.py) shows the fp64 ORACLE itself off by up to 3.8e-6 there
+# (cfg2: oracle -8.90583901, arbiter -8.90587314, CUDA -8.90587355), so against the oracle / the
+# reference-executed fixtures the lengthscale entries get LS_VS_ORACLE and everything else
+# HYPER_TOL; where an arbiter value exists (cfg2, cfg4, cfg5: tests/golden/arb_cfg*.npz) the CUDA
+# lengthscale gradient must agree with IT to LS_VS_ARBITER and replaces the oracle's entry in the
+# 1e-8 check of the packed gradient.
+HYPER_TOL = 1e-7
+LS_VS_ORACLE = 2e-5
+LS_VS_ARBITER = 2e-7
+
+
+def _hyper_tols(c):
+    from tests import baseline_configs as B
+    names = [k for k in c["order"] if k not in ("q_mu", "q_sqrt", "V")]
+    tol = []
+    for k in names:
+        tol += [LS_VS_ORACLE if k.endswith("lengthscales") else HYPER_TOL] * int(np.size(c["constrained"][k]))
+    return np.array(tol)
+
+
+def _arbitrated(name, c, g_ref):
+    """g_ref with the lengthscale entry replaced by the arbiter's, and that entry's index."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "arb_%s.npz" % name)
+    if not os.path.exists(path):
+        return g_ref, None, None
+    d = np.load(path)
+    off = 0
+    for k in c["order"]:
+        if k == "kern.lengthscales":
+            break
+        off += int(np.size(c["constrained"][k]))
+    g2 = np.array(g_ref)
+    g2[off] = float(d["g_ls"])
+    return g2, off, d
 
 
 @pytest.mark.parametrize("name", ["cfg2", "cfg3a", "cfg3b", "cfg4", "cfg5"])
 def test_baseline_config_full_size_against_oracle(name):
-    """The CUDA path at the exact BASELINE.json size against (a) the oracle run live on the same
-    host-generated inputs (every parameter block of the gradient) and (b) the committed compact
-    fixture of that oracle run (tests/golden/oc_*.npz)."""
+    """The CUDA path at the exact BASELINE.json size against (a) the committed compact fixture of
+    the oracle at that size (tests/golden/oc_*.npz), (b) the oracle run live on the same
+    host-generated inputs, every parameter block of the gradient at 1e-8, and (c) the longdouble
+    arbiter for the ill-conditioned lengthscale gradient."""
     from tests import baseline_configs as B
     from tests.golden.make_golden import oracle_in_chunks
     c = B.case(name, O.make_los_matrix, O.make_cos_theta)
@@ -374,15 +407,27 @@ def test_baseline_config_full_size_against_oracle(name):
     mask = B.hyper_mask(c)
     d = np.load(os.path.join(os.path.dirname(__file__), "golden", "oc_%s.npz" % name))
     assert np.array_equal(c["x"][:8], d["x_head"])
-    B.check_compact(f, g, d, mask, f_tol=1e-8, g_tol=1e-8, hyper_tol=HYPER_TOL)
+    B.check_compact(f, g, d, mask, f_tol=1e-8, g_tol=1e-8, hyper_tol=_hyper_tols(c))
     f_ref, g_ref = oracle_in_chunks(c["spec"], c["x"], c["eps"], 16 if name == "cfg3a" else 1 << 30)
     assert abs(f - f_ref) <= 1e-8 * abs(f_ref), (f, f_ref)
+    tols = _hyper_tols(c)
+    assert np.all(np.abs(g[mask] - g_ref[mask]) <= tols * np.abs(g_ref[mask])), (g[mask], g_ref[mask])
     for bname, a, b in _blocks(c["spec"]):
-        if mask[a]:
-            assert np.all(np.abs(g[a:b] - g_ref[a:b]) <= HYPER_TOL * np.abs(g_ref[a:b])), (bname, g[a:b], g_ref[a:b])
-        else:
+        if not mask[a]:
             assert rel_err(g[a:b], g_ref[a:b]) <= 1e-8, (bname, rel_err(g[a:b], g_ref[a:b]))
-    assert rel_err(g, g_ref) <= 1e-8
+    g_arb, i_ls, da = _arbitrated(name, c, g_ref)
+    if i_ls is not None:
+        e_cuda = abs(g[i_ls] - g_arb[i_ls]) / abs(g_arb[i_ls])
+        e_oracle = abs(g_ref[i_ls] - g_arb[i_ls]) / abs(g_arb[i_ls])
+        print("%s lengthscale gradient: CUDA %.10g oracle %.10g arbiter %.10g -> rel.err CUDA %.1e oracle %.1e; "
+              "f rel.err vs arbiter CUDA %.1e oracle %.1e" % (name, g[i_ls], g_ref[i_ls], g_arb[i_ls], e_cuda, e_oracle,
+                                                               abs(f - float(da["f"])) / abs(float(da["f"])),
+                                                               abs(f_ref - float(da["f"])) / abs(float(da["f"]))))
+        assert e_cuda <= LS_VS_ARBITER, (g[i_ls], g_arb[i_ls])
+        assert abs(f - float(da["f"])) <= 2e-9 * abs(float(da["f"]))
+        assert rel_err(g, g_arb) <= 1e-8
+    else:
+        assert rel_err(g, g_ref) <= 1e-8      # well-conditioned cores (n = 64 / Kronecker factors)
     if name == "cfg5":
         # the q_sqrt gradient's strict upper triangle is identically zero (GPinv/stvgp.py:157)
         n = c["spec"]["X"].shape[0]
@@ -411,7 +456,7 @@ def test_baseline_config_against_reference_executed_fixture(name):
     assert np.array_equal(c["x"][:8], d["x_head"])
     kw = {} if c["eps"] is None else {"eps": c["eps"]}
     f, g = m._objective(c["x"], **kw)
-    B.check_compact(f, np.array(g), d, B.hyper_mask(c), f_tol=1e-8, g_tol=1e-8, hyper_tol=1e-5 if "cfg5" in name else HYPER_TOL)
+    B.check_compact(f, np.array(g), d, B.hyper_mask(c), f_tol=1e-8, g_tol=1e-8, hyper_tol=_hyper_tols(c))
 
 
 def _arb_cases():
@@ -464,6 +509,135 @@ def test_samples_shapes_like_reference_tests():
     assert m.sample_F(10).shape == (10, 20, 1) and m.sample_Y(10).shape == (10, 20, 1)
     ma = make_abel_stvgp()
     assert ma.sample_F(100).shape == (100, 40, 1)
+
+
+def test_sample_F_and_sample_Y_values_against_oracle():
+    """sample_F / sample_Y (GPinv/stvgp.py:124-142, GPinv/gpmc.py:53-69, GPinv/likelihoods.py:78-82)
+    at fixed draws against the oracle's latent samples pushed through the likelihood transform:
+    Gaussian (identity), Abel (A exp f) and spectroscopic (three latent functions)."""
+    gpmc, kernels, kronecker, likelihoods, mean_functions, stvgp = _gp()
+    rng = np.random.RandomState(11)
+
+    def check(m, S):
+        spec = spec_from_model(m)
+        x = perturbed_state(m, 0.1)
+        m.set_state(x)
+        n, R = m.num_data, m.num_latent
+        eps = rng.randn(R, S, n)
+        P, f, _ = O.latent_samples(spec, x, eps)
+        F_ref = O.sample_F_transform(spec, P, f).detach().numpy()
+        F = m.sample_F(S, eps=eps)
+        assert F.shape == F_ref.shape
+        assert np.allclose(F, F_ref, rtol=1e-9, atol=1e-11), np.abs(F - F_ref).max()
+        noise = rng.randn(*F_ref.shape)
+        Yref = F_ref + np.sqrt(float(P["likelihood.variance"].reshape(-1)[0])) * noise
+        Ys = m.sample_Y(S, eps=eps, noise=noise)
+        assert np.allclose(Ys, Yref, rtol=1e-9, atol=1e-11)
+        # without fixed draws: same mean function of the latent samples, unit-variance noise
+        Yr = m.sample_Y(4000 // F_ref[0].size + 2, eps=None)
+        assert Yr.shape[1:] == F_ref.shape[1:] and np.all(np.isfinite(Yr))
+
+    X = np.linspace(0., 1., 20)[:, None]
+    Y = np.sin(3. * X) + rng.randn(20, 1) * 0.1
+    check(stvgp.StVGP(X, Y, kern=kernels.RBF(1, 1), likelihood=likelihoods.Gaussian()), 7)
+    check(make_abel_stvgp(30, 40, 10), 9)
+    r, A, cosT, lam, y = spec_data(12, 9, 7)
+    check(stvgp.StVGP(r[:, None], y, kernels.Stack([kernels.RBF_csym(1, 2), kernels.RBF_casym(1, 1)]),
+                      likelihoods.SpecAbelLikelihood(A, cosT, lam),
+                      mean_functions.Stack([mean_functions.Constant(2), mean_functions.Zero(1)]), num_latent=3), 5)
+    # GPMC: the current state is one posterior sample
+    r, z, A, y = abel_data(30, 40)
+    mc = gpmc.GPMC(r[:, None], y[:, None], kernels.RBF_csym(1, 1), likelihoods.AbelLikelihood(A), mean_functions.Constant(1))
+    x = perturbed_state(mc, 0.3)
+    mc.set_state(x)
+    spec = spec_from_model(mc)
+    P = O.unpack(spec, O._t(x))
+    L = O._kern_chol(spec["kern"], "kern", P, O._t(spec["X"]))
+    Fl = (torch.matmul(L.permute(2, 0, 1), P["V"].T[:, :, None]).squeeze(-1).T + P["mean_function.c"][None, :])[None]
+    F_ref = O.sample_F_transform(spec, P, Fl).numpy()
+    assert np.allclose(mc.sample_F(), F_ref, rtol=1e-9, atol=1e-11)
+    noise = rng.randn(*F_ref.shape)
+    assert np.allclose(mc.sample_Y(noise=noise), F_ref + np.sqrt(float(P["likelihood.variance"][0])) * noise, rtol=1e-9)
+
+
+def test_reference_style_custom_kernel_and_cholesky_override():
+    """A user kernel written against the REFERENCE plugin signature ``_Kcore(self, X, X2=None)``
+    (GPinv/kernels.py:31-40) in torch ops, and one that overrides ``Cholesky`` (as the reference's
+    RBF2D does, GPinv/kronecker.py:49-66), must drop in: same ELBO and gradient as the built-in RBF."""
+    gpmc, kernels, kronecker, likelihoods, mean_functions, stvgp = _gp()
+    from gpinv_b200.settings import settings
+
+    class MyRBF(kernels.Stationary):
+        def _Kcore(self, X, X2=None):
+            X, X2 = self._slice(X, X2)
+            return torch.exp(-self.square_dist(X, X2) / 2)
+
+    class MyCholRBF(kernels.RBF):
+        def Cholesky(self, X):
+            core = torch.exp(-self.square_dist(X, None) / 2)
+            core = core + settings.numerics.jitter_level * torch.eye(X.shape[0], dtype=core.dtype, device=core.device)
+            chol = torch.linalg.cholesky(core)
+            return chol[:, :, None] * torch.sqrt(self.variance)[None, None, :]
+
+    n, S = 60, 9
+    X = np.linspace(0, 6, n)[:, None]
+    Y = np.sin(X) + 0.3 * np.random.RandomState(0).randn(n, 1)
+    eps = np.random.RandomState(2).randn(1, S, n)
+    res = []
+    for cls in (kernels.RBF, MyRBF, MyCholRBF):
+        m = stvgp.StVGP(X, Y, cls(1, 1), likelihoods.Gaussian(), num_samples=S)
+        m.kern.lengthscales = 0.7
+        xs = perturbed_state(m, 0.05)
+        f, g = m._objective(xs, eps=eps)
+        m.set_state(xs)
+        mu, var = m.predict_f(X[:7] + 0.01)
+        res.append((f, g, mu, var))
+    for f, g, mu, var in res[1:]:
+        assert abs(f - res[0][0]) <= 1e-9 * abs(res[0][0])
+        assert rel_err(g, res[0][1]) <= 1e-7
+        assert np.allclose(mu, res[0][2], rtol=1e-7, atol=1e-9) and np.allclose(var, res[0][3], rtol=1e-6, atol=1e-9)
+
+
+def test_cuda_graph_follows_data_and_fixed_parameter_changes():
+    """A captured evaluation must not replay stale data: new Y / A of the same shape, a value
+    assigned to a fixed Param, or fixing a Param between replays all show up in the result."""
+    gpmc, kernels, kronecker, likelihoods, mean_functions, stvgp = _gp()
+    m = make_abel_stvgp(30, 40, 10)
+    m.likelihood.variance.fixed = True
+    x = perturbed_state(m)
+    eps = np.random.RandomState(2).randn(1, 10, 30)
+
+    def both():
+        fe, ge = m.enable_cuda_graph(False)._objective(x, eps=eps)
+        m._use_graph = True           # keep the captured graphs (enable_cuda_graph() would drop them)
+        fg, gg = m._objective(x, eps=eps)
+        fg, gg = m._objective(x, eps=eps)
+        assert same_evaluation(fg, gg, fe, ge, 3, f_tol=1e-11, q_tol=1e-11), (fg, fe)
+        return fe
+
+    m.enable_cuda_graph()
+    f0 = both()
+    m.Y = m.Y.value + 0.05                       # DataHolder.set_data, same shape
+    f1 = both()
+    assert abs(f1 - f0) > 1e-6 * abs(f0)
+    m.likelihood.Amat = 1.01 * m.likelihood.Amat.value
+    f2 = both()
+    assert abs(f2 - f1) > 1e-6 * abs(f1)
+    m.likelihood.variance = 0.5                  # fixed Param re-assigned
+    f3 = both()
+    assert abs(f3 - f2) > 1e-6 * abs(f2)
+    m.kern.variance.fixed = True                 # |x| shrinks by one
+    x = np.delete(x, 1)
+    both()
+
+
+def test_dist_attach_refuses_models_without_samples():
+    gpmc, kernels, kronecker, likelihoods, mean_functions, stvgp = _gp()
+    from gpinv_b200 import dist as gdist
+    r, z, A, y = abel_data(30, 40)
+    mc = gpmc.GPMC(r[:, None], y[:, None], kernels.RBF_csym(1, 1), likelihoods.AbelLikelihood(A), mean_functions.Constant(1))
+    with pytest.raises(TypeError, match="replicas"):
+        gdist.attach(mc, gdist.DistContext(rank=0, world_size=2))
 
 
 def test_cholesky_failure_raises():
