@@ -11,7 +11,8 @@ import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgpinv_sm100.so")
+# GPINV_LIB_PATH: load an alternative build of the library (kernel experiments only)
+LIB_PATH = os.environ.get("GPINV_LIB_PATH") or os.path.join(_HERE, "lib", "libgpinv_sm100.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gpinv_b200.h")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 

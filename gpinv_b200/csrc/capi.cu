@@ -206,7 +206,7 @@ int gpinv_chol_core_f64(const double* X, int n, int D, int ldx, const double* ls
 }
 
 size_t gpinv_chol_core_bwd_ws_bytes(int n, int D) {
-  return (size_t)4 * n * n * sizeof(double) + kbuild_ws_bytes(n, n, D);
+  return (size_t)n * n * sizeof(double) + potrf_bwd_inv_ws_bytes(n) + kbuild_ws_bytes(n, n, D);
 }
 
 int gpinv_chol_core_bwd_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
@@ -214,8 +214,8 @@ int gpinv_chol_core_bwd_f64(const double* X, int n, int D, int ldx, const double
                             double* ls_bar, void* ws, void* stream) {
   if (n <= 0 || D <= 0 || ldl < n || ldlb < n) return GPINV_ERR_ARG;
   double* Ab = static_cast<double*>(ws);              // n x n: tril(Lbar), then the Murray-lower Kbar
-  double* sweep_ws = Ab + (size_t)n * n;              // 3 n^2
-  double* kws = sweep_ws + (size_t)3 * n * n;
+  double* sweep_ws = Ab + (size_t)n * n;              // potrf_bwd_inv_ws_bytes(n)
+  double* kws = sweep_ws + potrf_bwd_inv_ws_bytes(n) / sizeof(double);
   int rc = tril_copy_f64(Lbar, ldlb, Ab, n, n, ST(stream));
   if (rc) return rc;
   rc = potrf_bwd_hybrid_ex_f64(L, ldl, Ab, n, n, sweep_ws, 1, 0, ST(stream));

@@ -1,5 +1,5 @@
 // Host-side dispatch for the DMMA GEMM template (see gemm.cuh).
-#include "gemm.cuh"
+#include "gemm_tma.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -10,16 +10,14 @@ namespace {
 
 template <class Cfg, int LA, int LB, unsigned EF>
 int launch_persistent(const GemmParams& p, dim3 grid, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set[64] = {};     // the attribute is per device
   auto kern = gemm_dmma_persistent_kernel<Cfg, LA, LB, EF>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_last_error(cudaGetErrorString(e));
-      return GPINV_ERR_CUDA;
-    }
-    attr_set = true;
+  int dev = 0;
+  GPINV_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
+    GPINV_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[dev] = true;
   }
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   GPINV_CHECK_LAUNCH();
@@ -28,16 +26,14 @@ int launch_persistent(const GemmParams& p, dim3 grid, cudaStream_t stream) {
 
 template <class Cfg, int LA, int LB, unsigned EF>
 int launch_inst(const GemmParams& p, dim3 grid, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set[64] = {};     // the attribute is per device
   auto kern = gemm_dmma_kernel<Cfg, LA, LB, EF>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_last_error(cudaGetErrorString(e));
-      return GPINV_ERR_CUDA;
-    }
-    attr_set = true;
+  int dev = 0;
+  GPINV_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
+    GPINV_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[dev] = true;
   }
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   GPINV_CHECK_LAUNCH();
@@ -77,6 +73,30 @@ template <class Cfg>
 int dispatch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream);
 
 }  // namespace
+
+bool gemm_workspace_for_device(void** ptr, size_t* bytes) {
+  WsReg* w = ws_for_device();
+  if (!w) return false;
+  *ptr = w->ptr;
+  *bytes = w->bytes;
+  return true;
+}
+
+// Tile configuration for the TMA / stream-K path: the 128x128 tile whenever the problem holds enough
+// k-tile work units to give every SM a useful share (stream-K fills the machine regardless of the
+// tile count), the 64x64 tile (3 CTAs/SM) for short-K or tiny problems.
+static bool use_small_tma(const GemmParams& p, bool lower) {
+  static const char* force = getenv("GPINV_TMA_FORCE");     // debugging: big | small
+  if (force && force[0] == 'b') return false;
+  if (force && force[0] == 's') return true;
+  if (p.force_cfg == 1 || p.force_cfg == 3) return false;
+  if (p.force_cfg == 2) return true;
+  const int batch = p.batch > 1 ? p.batch : 1;
+  const long long tiles = (long long)tiles_of(p.M, p.N, 128, lower) * batch;
+  const long long units = tiles * cdiv(p.K, 16) / ((p.kmode != 0) ? 2 : 1);
+  if (p.K <= 128) return tiles < 600;
+  return units < 148 * 16;
+}
 
 void gemm_set_workspace(void* ptr, size_t bytes) {
   int dev = 0;
@@ -158,7 +178,14 @@ int gemm_launch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) 
     p.vecB = p.vecB && (p.strideB % 2 == 0);
     p.vecO = p.vecO && (p.strideO % 2 == 0);
   }
+  p.vecO2 = (p.out2 != nullptr) && aligned16(p.out2) && (p.ldo2 % 2 == 0);
   const bool lower = (ef & EF_LOWER) != 0;
+  {
+    // Blackwell path: TMA-staged operands, mbarrier ring, persistent stream-K partition
+    int rc_tma = GPINV_OK;
+    GemmParams pt = p;
+    if (gemm_tma_try_launch(la, lb, ef, pt, use_small_tma(p, lower), stream, &rc_tma)) return rc_tma;
+  }
   const bool small = use_small(p, lower);
   // ---- k-split planning (big tiles only): list-schedule the CTAs in launch order on the SMs
   // with a per-CTA time model and keep the split factor with the smallest makespan.  Fixes wave

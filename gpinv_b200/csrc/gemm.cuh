@@ -68,6 +68,7 @@ struct GemmParams {
   double* ws;
   int* ws_cnt;
   int vecA, vecB, vecO;  // 16-byte alignment of operands / output rows
+  int vecO2;             // ... of the second output (EF_EXP2)
   // batching over blockIdx.z (element strides; 0 = shared operand)
   int batch;
   long long strideA, strideB, strideO, strideCin;

@@ -769,7 +769,10 @@ static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cuda
   return GPINV_OK;
 }
 
-size_t potrf_bwd_inv_ws_bytes(int n) { return (size_t)3 * n * n * sizeof(double); }
+size_t potrf_bwd_inv_ws_bytes(int n) {
+  // W, S1, S2 (n x n each) + S3, S4 (block x block each, block <= 1024 by default)
+  return ((size_t)3 * n * n + (size_t)2 * 2048 * 2048) * sizeof(double);
+}
 
 // Ab: Lbar (any upper part is ignored) on entry, full symmetric dObj/dA on exit.
 int potrf_bwd_inv_f64(const double* L, int ldl, double* Ab, int ldab, int n, double* ws,
@@ -853,6 +856,55 @@ static int bwd_block() {
 int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int n, double* ws,
                             int ab_is_tril, int finalize, cudaStream_t st);
 
+// Reverse of ONE diagonal block by the inverse formula, with both triangular solves refined:
+//   G = sym(L^-T Phi(L^T Lbar) L^-1),   W ~ L^-1 explicit.
+//   stage 1   T  = P L^-1  :  T0 = tril(P W),  R1 = P - tril(T0 L),  T = T0 + tril(R1 W)
+//   stage 2   H  = L^-T T  :  H0 = W^T T,      R2 = T - L^T H0,      H = H0 + W^T R2
+//   Dbar <- tril(H) + tril(H^T)  with the diagonal halved  (Murray's convention: strict lower = 2 G)
+// Products with an explicit inverse are not backward stable; inside the blocked sweep their error
+// (~cond(L_bb) eps relative to the block) feeds the later blocks and the lengthscale reduction, a sum
+// that cancels to ~1e-6 of its terms.  Measured against the longdouble arbiter (oracle/arbiter.py)
+// at cfg4 (n = 2048, two blocks): unrefined 3.8e-6, substitution-based leaf 1.1e-8, refined: see
+// DESIGN.md.  GPINV_LEAF_REFINE = bitmask (1: stage 1, 2: stage 2; default 3).
+static int leaf_reverse_refined(const double* Lbb, int ldl, const double* Wbb, int ldw, double* Dbar,
+                                int ldab, int bw, double* P, double* T, double* H, double* R2,
+                                cudaStream_t st) {
+  static const int refine = getenv("GPINV_LEAF_REFINE") ? atoi(getenv("GPINV_LEAF_REFINE")) : 3;
+  int rc;
+  rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, Lbb, ldl, Dbar, ldab, 0.0, nullptr, 0, P, bw,
+               4, st);                                          // P = tril(L^T Lbar)
+  if (rc) return rc;
+  scale_diag_kernel<<<cdiv(bw, 256), 256, 0, st>>>(P, bw, bw, 0.5);   // Phi
+  GPINV_CHECK_LAUNCH();
+  if (refine & 2) GPINV_TRY(cudaMemsetAsync(T, 0, (size_t)bw * bw * sizeof(double), st));   // H0 reads all of T
+  rc = gemm_ws(LK, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, P, bw, Wbb, ldw, 0.0, nullptr, 0, T, bw, 5, st);
+  if (rc) return rc;                                            // T0 = tril(P W)
+  if (refine & 1) {
+    rc = gemm_ws(LK, LMN, EF_BETA | EF_LOWER, bw, bw, bw, -1.0, T, bw, Lbb, ldl, 1.0, P, bw, P, bw, 5, st);
+    if (rc) return rc;                                          // R1 = P - tril(T0 L)     (in place of P)
+    rc = gemm_ws(LK, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, P, bw, Wbb, ldw, 1.0, T, bw, T, bw, 5, st);
+    if (rc) return rc;                                          // T = T0 + tril(R1 W)
+  }
+  if (!(refine & 2)) {
+    rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, Wbb, ldw, T, bw, 0.0, nullptr, 0, Dbar, ldab, 4, st);
+    if (rc) return rc;                                          // tril(W^T T)
+  } else {
+    rc = gemm_ws(LMN, LMN, EF_BETA, bw, bw, bw, 1.0, Wbb, ldw, T, bw, 0.0, nullptr, 0, H, bw, 4, st);
+    if (rc) return rc;                                          // H0 = W^T T  (full; k >= row)
+    rc = gemm_ws(LMN, LMN, EF_BETA, bw, bw, bw, -1.0, Lbb, ldl, H, bw, 1.0, T, bw, R2, bw, 4, st);
+    if (rc) return rc;                                          // R2 = T - L^T H0  (full)
+    rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, Wbb, ldw, R2, bw, 1.0, H, bw, Dbar, ldab, 4, st);
+    if (rc) return rc;                                          // tril(H0 + W^T R2) = tril(H)
+    rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, R2, bw, Wbb, ldw, 1.0, Dbar, ldab, Dbar, ldab, 2, st);
+    if (rc) return rc;                                          // + tril(R2^T W)      (k >= column)
+  }
+  rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, T, bw, Wbb, ldw, 1.0, Dbar, ldab, Dbar, ldab, 4, st);
+  if (rc) return rc;                                            // + tril(T^T W) = tril(H0^T)
+  scale_diag_kernel<<<cdiv(bw, 256), 256, 0, st>>>(Dbar, bw, ldab, 0.5);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
 int potrf_bwd_hybrid_f64(const double* L, int ldl, double* Ab, int ldab, int n, double* ws,
                          cudaStream_t st) {
   return potrf_bwd_hybrid_ex_f64(L, ldl, Ab, ldab, n, ws, 0, 1, st);
@@ -866,9 +918,14 @@ int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int 
   double* W = ws;                       // n x n, only the m x m diagonal blocks are non-zero
   double* S1 = W + (size_t)n * n;       // scratch: Cbar W_bb  /  P
   double* S2 = S1 + (size_t)n * n;      // scratch: T1  /  symmetrised block
-  GPINV_TRY(cudaMemsetAsync(W, 0, (size_t)n * n * sizeof(double), st));
-  int rc = trtri_f64(L, ldl, W, S1, n, st, m);
-  if (rc) return rc;
+  double* S3 = S2 + (size_t)n * n;      // scratch of the refined diagonal-block reverse (m x m each)
+  double* S4 = S3 + (size_t)m * m;
+  int rc = GPINV_OK;
+  if (n > pcfg::NB) {     // (a single 64-wide block is reversed by substitution: no inverse needed)
+    GPINV_TRY(cudaMemsetAsync(W, 0, (size_t)n * n * sizeof(double), st));
+    rc = trtri_f64(L, ldl, W, S1, n, st, m);
+    if (rc) return rc;
+  }
   dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n, 8));
   if (!ab_is_tril) {
     zero_upper_kernel<<<grd, blk, 0, st>>>(Ab, n, ldab);
@@ -892,10 +949,17 @@ int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int 
       // the longdouble arbiter (oracle/arbiter.py) the unrefined sweep was off by 7.6e-6 at n = 2048
       // where the substitution-based sweep and the refined one are at ~1e-8.  Costs two more
       // r x m x m triangular GEMMs per block column; the copy-back of X disappears into the last one.
-      rc = gemm_ws(LK, LMN, EF_BETA, r, bw, bw, 1.0, Cb, ldab, Wbb, n, 0.0, nullptr, 0, S1, bw, 2, st);
-      if (rc) return rc;
+      static const bool trsm_subst0 = (getenv("GPINV_BWD_TRSM_SUBST") != nullptr);
+      if (!trsm_subst0) {
+        rc = gemm_ws(LK, LMN, EF_BETA, r, bw, bw, 1.0, Cb, ldab, Wbb, n, 0.0, nullptr, 0, S1, bw, 2, st);
+        if (rc) return rc;
+      }
       static const bool no_refine = (getenv("GPINV_BWD_NO_REFINE") != nullptr);
-      if (no_refine) {
+      static const bool trsm_subst = (getenv("GPINV_BWD_TRSM_SUBST") != nullptr);   // experiment
+      if (trsm_subst) {
+        rc = trsm_rln_blocked(L, ldl, Ab, ldab, s, e, e, n, st);
+        if (rc) return rc;
+      } else if (no_refine) {
         GPINV_TRY(cudaMemcpy2DAsync(Cb, (size_t)ldab * sizeof(double), S1, (size_t)bw * sizeof(double),
                                     (size_t)bw * sizeof(double), r, cudaMemcpyDeviceToDevice, st));
       } else {
@@ -933,25 +997,21 @@ int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int 
       if (rc) return rc;
     }
     // diagonal block: Dbar (holding Lbar_bb) -> Murray-convention tril of the block gradient
-    {
-      double* P = S1;
-      double* T1 = S2;
-      rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, Lbb, ldl, Dbar, ldab, 0.0, nullptr, 0,
-                   P, bw, 4, st);                                   // P = tril(L^T Lbar)
+    static const bool leaf_murray = (getenv("GPINV_BWD_LEAF_MURRAY") != nullptr);   // experiment
+    if (leaf_murray) {
+      rc = set_smem_attrs();
       if (rc) return rc;
-      scale_diag_kernel<<<cdiv(bw, 256), 256, 0, st>>>(P, bw, bw, 0.5);   // Phi
+      rc = potrf_bwd_range(L, ldl, Ab, ldab, s, e, pcfg::NBO, true, S2, st);
+      if (rc) return rc;
+    } else if (bw <= pcfg::NB) {
+      // a single 64-wide block: the level-2 reverse in shared memory (substitution, one launch)
+      rc = set_smem_attrs();
+      if (rc) return rc;
+      leaf_rev_kernel<<<1, 256, pcfg::LEAF_SMEM, st>>>(L, ldl, Ab, ldab, s, bw);
       GPINV_CHECK_LAUNCH();
-      rc = gemm_ws(LK, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, P, bw, Wbb, n, 0.0, nullptr, 0, T1, bw,
-                   5, st);                                          // T1 = tril(P W)
+    } else {
+      rc = leaf_reverse_refined(Lbb, ldl, Wbb, n, Dbar, ldab, bw, S1, S2, S3, S4, st);
       if (rc) return rc;
-      rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, Wbb, n, T1, bw, 0.0, nullptr, 0, Dbar,
-                   ldab, 4, st);                                    // tril(W^T T1)
-      if (rc) return rc;
-      rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, T1, bw, Wbb, n, 1.0, Dbar, ldab, Dbar,
-                   ldab, 4, st);                                    // + tril(T1^T W)
-      if (rc) return rc;
-      scale_diag_kernel<<<cdiv(bw, 256), 256, 0, st>>>(Dbar, bw, ldab, 0.5);
-      GPINV_CHECK_LAUNCH();
     }
     if (s > 0) {
       double* Rb = Ab + (size_t)s * ldab;               // Rbar: block rows, columns [0, s)

@@ -45,6 +45,26 @@ def check_gemm():
     A = torch.randn(300, 77, generator=g, dtype=torch.float64)
     out = ops.gemm(A.to(dev), A.to(dev), False, True, True)
     report("gemm lower 300x300x77", rel(torch.tril(out), torch.tril(A @ A.T)), 1e-13)
+    # many tiles per CTA (persistent stream-K partition: whole tiles, shared tiles, ragged edges)
+    gd = torch.Generator(device=dev).manual_seed(1)
+    for (m, n, k) in [(2048, 2048, 512), (1000, 3000, 700), (4096, 1024, 4096), (1024, 8192, 2048), (2500, 2500, 256),
+                      (130, 140, 20000), (64, 64, 50000)]:
+        for ta in (False, True):
+            for tb in (False, True):
+                A = torch.randn((k, m) if ta else (m, k), generator=gd, dtype=torch.float64, device=dev)
+                B = torch.randn((n, k) if tb else (k, n), generator=gd, dtype=torch.float64, device=dev)
+                ref = torch.matmul(A.T if ta else A, B.T if tb else B)
+                out = ops.gemm(A, B, ta, tb, False)
+                report("gemm %dx%dx%d ta=%d tb=%d" % (m, n, k, ta, tb), rel(out, ref), 1e-12)
+                out2 = ops.gemm(A, B, ta, tb, False)
+                report("   ... repeat bitwise", 0.0 if torch.equal(out, out2) else 1.0, 0.5)
+    for (m, k) in [(2500, 256), (3072, 1000), (4096, 64)]:
+        A = torch.randn(m, k, generator=gd, dtype=torch.float64, device=dev)
+        out = ops.gemm(A, A, False, True, True)
+        report("gemm lower %dx%dx%d" % (m, m, k), rel(torch.tril(out), torch.tril(A @ A.T)), 1e-12)
+        At = A.T.contiguous()
+        out = ops.gemm(At, At, True, False, True)
+        report("gemm lower TN %dx%dx%d" % (m, m, k), rel(torch.tril(out), torch.tril(A @ A.T)), 1e-12)
 
 
 def check_kcore():
@@ -209,7 +229,8 @@ def check_liks():
 
 if __name__ == "__main__":
     t0 = time.time()
-    for fn in (check_gemm, check_kcore, check_potrf, check_trsm, check_sample, check_liks):
+    names = sys.argv[1:] or ["check_gemm", "check_kcore", "check_potrf", "check_trsm", "check_sample", "check_liks"]
+    for fn in [globals()[nm] for nm in names]:
         try:
             fn()
             torch.cuda.synchronize()
