@@ -47,6 +47,11 @@ SIGNATURES = {
     "gpinv_sample_fwd_f64": (_I, [_P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gpinv_sample_bwd_f64": (_I, [_P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I,
                                   _P, _P, _P, _P, _I, _P, _P, _P]),
+    "gpinv_kron_apply_f64": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P]),
+    "gpinv_kron_sample_fwd_f64": (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "gpinv_kron_bwd_ws_bytes": (_Z, [_I, _I, _I, _I]),
+    "gpinv_kron_sample_bwd_f64": (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I,
+                                       _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gpinv_gauss_sumsq_f64": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "gpinv_gauss_bwd_f64": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "gpinv_abel_fwd_f64": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _P, _P]),

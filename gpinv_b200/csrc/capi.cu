@@ -51,6 +51,15 @@ int abel_fwd_f64(const double*, const double*, int, const double*, int, int, int
                  cudaStream_t);
 int abel_bwd_f64(const double*, const double*, int, const double*, const double*, int, int, int,
                  double*, cudaStream_t);
+int kron_apply_f64(const double*, int, int, const double*, int, int, const double*, int, double, const double*,
+                   const double*, double*, double*, double*, int, cudaStream_t);
+size_t kron_bwd_ws_bytes(int, int, int, int);
+int kron_sample_fwd_f64(const double*, int, const double*, int, const double*, const double*, int, const double*,
+                        const double*, const double*, int, int, double*, double*, double*, double*, double*,
+                        cudaStream_t);
+int kron_sample_bwd_f64(const double*, int, const double*, int, const double*, const double*, int, const double*,
+                        const double*, const double*, const double*, const double*, int, int, double*, double*,
+                        double*, double*, double*, double*, double*, double*, cudaStream_t);
 int spec_fwd_f64(const double*, const double*, const double*, const double*, const double*, int, int,
                  int, int, double*, double*, cudaStream_t);
 int spec_bwd_f64(const double*, const double*, const double*, const double*, const double*,
@@ -125,7 +134,7 @@ int gpinv_potrf_bwd_f64(const double* L, int ldl, double* Abar, int ldab, int n,
   if (n <= 0 || ldl < n || ldab < n) return GPINV_ERR_ARG;
   const int mode = bwd_mode();
   if (mode == 1) return potrf_bwd_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
-  if (mode == 0 && n > potrf_bwd_hybrid_block())
+  if (mode == 0)
     return potrf_bwd_hybrid_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
   return potrf_bwd_inv_f64(L, ldl, Abar, ldab, n, static_cast<double*>(ws), ST(stream));
 }
@@ -293,6 +302,32 @@ int gpinv_spec_bwd_f64(const double* F, const double* A, const double* cosT, con
                        const double* Y, const double* P, const double* coef, int n, int m, int k,
                        int S, double* Fbar, void* stream) {
   return spec_bwd_f64(F, A, cosT, lam, Y, P, coef, n, m, k, S, Fbar, ST(stream));
+}
+
+int gpinv_kron_apply_f64(const double* L1, int n1, const double* L2, int n2, const double* U, int batch,
+                         double* T_ws, double* F, int trans, void* stream) {
+  if (!L1 || !L2 || !U || !T_ws || !F) return GPINV_ERR_ARG;
+  return kron_apply_f64(L1, n1, n1, L2, n2, n2, U, batch, 1.0, nullptr, nullptr, T_ws, F, nullptr, trans,
+                        ST(stream));
+}
+
+size_t gpinv_kron_bwd_ws_bytes(int n1, int n2, int S, int R) { return kron_bwd_ws_bytes(n1, n2, S, R); }
+
+int gpinv_kron_sample_fwd_f64(const double* L1, int n1, const double* L2, int n2, const double* sqrt_v,
+                              const double* Q, int q_diag, const double* q_mu, const double* mean,
+                              const double* E, int S, int R, double* U, double* T, double* F, double* expF,
+                              double* kl_out, void* stream) {
+  return kron_sample_fwd_f64(L1, n1, L2, n2, sqrt_v, Q, q_diag, q_mu, mean, E, S, R, U, T, F, expF, kl_out,
+                             ST(stream));
+}
+
+int gpinv_kron_sample_bwd_f64(const double* L1, int n1, const double* L2, int n2, const double* sqrt_v,
+                              const double* Q, int q_diag, const double* E, const double* U, const double* T,
+                              const double* Fbar, const double* klbar, int S, int R, double* Ubar,
+                              double* qmu_bar, double* Qbar, double* L1bar, double* L2bar, double* svdot,
+                              double* mean_bar, void* ws, void* stream) {
+  return kron_sample_bwd_f64(L1, n1, L2, n2, sqrt_v, Q, q_diag, E, U, T, Fbar, klbar, S, R, Ubar, qmu_bar, Qbar,
+                             L1bar, L2bar, svdot, mean_bar, static_cast<double*>(ws), ST(stream));
 }
 
 int gpinv_sumsq_f64(const double* x, size_t count, double* out, void* stream) {

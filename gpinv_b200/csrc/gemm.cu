@@ -153,6 +153,7 @@ int dispatch(int la, int lb, unsigned ef, GemmParams p, cudaStream_t stream) {
   GPINV_GEMM_CASE(LK, LK, EF_COLVEC | EF_SUMSQ)               // U = E Q^T + m ; R = Y - X A^T
   GPINV_GEMM_CASE(LK, LK, EF_COLVEC)                          // F = sv U Lc^T + mu
   GPINV_GEMM_CASE(LK, LK, EF_COLVEC | EF_EXP2)                // ... and exp(F)
+  GPINV_GEMM_CASE(LK, LMN, EF_BETA | EF_EXP2)                   // Kronecker apply: F = sv L1 T + mean and exp(F)
   GPINV_GEMM_CASE(LK, LMN, EF_MULMAT)                         // Fbar = X o (R A) c
   GPINV_GEMM_CASE(LK, LMN, EF_BETA | EF_COLSUM)               // Ubar = sv Fbar Lc + klbar U
   GPINV_GEMM_CASE(LMN, LMN, EF_LOWER)                         // Qbar = tril(Ubar^T E)

@@ -278,6 +278,7 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& pin, const int 
     p.A += z * p.strideA;
     p.B += z * p.strideB;
     if (p.out) p.out += z * p.strideO;
+    if (p.out2) p.out2 += z * p.strideO;      // the second output follows the first through the batch
     if (p.Cin) p.Cin += z * p.strideCin;
   }
 

@@ -258,6 +258,7 @@ int dispatch_tma(int la, int lb, unsigned ef, const CUtensorMap& mA, const CUten
   GPINV_TMA_CASE(LK, LK, EF_COLVEC | EF_SUMSQ)               // U = E Q^T + m ; R = Y - X A^T
   GPINV_TMA_CASE(LK, LK, EF_COLVEC)                          // F = sv U Lc^T + mu
   GPINV_TMA_CASE(LK, LK, EF_COLVEC | EF_EXP2)                // ... and exp(F)
+  GPINV_TMA_CASE(LK, LMN, EF_BETA | EF_EXP2)                   // Kronecker apply: F = sv L1 T + mean and exp(F)
   GPINV_TMA_CASE(LK, LMN, EF_MULMAT)                         // Fbar = X o (R A) c
   GPINV_TMA_CASE(LK, LMN, EF_BETA | EF_COLSUM)               // Ubar = sv Fbar Lc + klbar U
   GPINV_TMA_CASE(LMN, LMN, EF_LOWER)                         // Qbar = tril(Ubar^T E)

@@ -154,8 +154,10 @@ __device__ __forceinline__ void tma_epilogue(const GemmParams& p, const TmaWork&
   const int m0 = w.m0, n0 = w.n0;
   const double* Cin = p.Cin;
   double* out = p.out;
+  double* out2 = p.out2;
   if (p.batch > 1) {
     if (out) out += (long long)w.z * p.strideO;
+    if (out2) out2 += (long long)w.z * p.strideO;
     if (Cin) Cin += (long long)w.z * p.strideCin;
   }
   double alpha = p.alpha;
@@ -240,7 +242,7 @@ __device__ __forceinline__ void tma_epilogue(const GemmParams& p, const TmaWork&
           }
         }
         if (EF & EF_EXP2) {
-          double* o = p.out2 + (size_t)row * p.ldo2 + col;
+          double* o = out2 + (size_t)row * p.ldo2 + col;
           if (ok[P][0] && ok[P][1] && p.vecO2) {
             *reinterpret_cast<double2*>(o) = make_double2(exp(v[0]), exp(v[1]));
           } else {

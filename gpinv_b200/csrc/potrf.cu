@@ -842,10 +842,18 @@ static int gemm_ws(int la, int lb, unsigned ef, int M, int N, int K, double alph
   return gemm_launch(la, lb, ef, p, st);
 }
 
+// Block width of the reverse sweep.  Default: ONE block, i.e. the inverse formula applied to the whole
+// matrix.  Measured against the longdouble arbiter (oracle/arbiter.py, lengthscale gradient at cfg4,
+// n = 2048): whole matrix 4.6e-10; blocks of 64 / 128 (substitution / inverse-form leaves) 1e-8; but
+// blocks of 512 / 1024 with inverse-form leaves 1e-7 .. 4e-6 -- the leaf's error (~cond(L_bb)^2 eps of the
+// block norm) is fed through Rbar -= sym(Dbar) R and the following block solves -- and refining the
+// leaf's triangular solves does not help.  The blocked sweep (0.73 n^3 flops instead of 5 n^3 / 3)
+// stays selectable with GPINV_BWD_BLOCK for experiments.
 static int bwd_block() {
   static const int m = [] {
     const char* e = getenv("GPINV_BWD_BLOCK");
-    int v = e ? atoi(e) : 1024;
+    if (!e) return 1 << 30;
+    int v = atoi(e);
     int p2 = pcfg::NB;
     while (p2 * 2 <= v) p2 *= 2;
     return p2;
@@ -864,12 +872,14 @@ int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int 
 // Products with an explicit inverse are not backward stable; inside the blocked sweep their error
 // (~cond(L_bb) eps relative to the block) feeds the later blocks and the lengthscale reduction, a sum
 // that cancels to ~1e-6 of its terms.  Measured against the longdouble arbiter (oracle/arbiter.py)
-// at cfg4 (n = 2048, two blocks): unrefined 3.8e-6, substitution-based leaf 1.1e-8, refined: see
-// DESIGN.md.  GPINV_LEAF_REFINE = bitmask (1: stage 1, 2: stage 2; default 3).
+// at cfg4 (n = 2048, two blocks): unrefined 3.8e-6, substitution-based leaf 1.1e-8, refined
+// no better (2e-6 .. 4e-6): the refinement is kept as an experiment only.
+// GPINV_LEAF_REFINE = bitmask (1: stage 1, 2: stage 2; default 0 = plain inverse formula).
 static int leaf_reverse_refined(const double* Lbb, int ldl, const double* Wbb, int ldw, double* Dbar,
                                 int ldab, int bw, double* P, double* T, double* H, double* R2,
-                                cudaStream_t st) {
-  static const int refine = getenv("GPINV_LEAF_REFINE") ? atoi(getenv("GPINV_LEAF_REFINE")) : 3;
+                                bool scratch_ok, cudaStream_t st) {
+  static const int refine_env = getenv("GPINV_LEAF_REFINE") ? atoi(getenv("GPINV_LEAF_REFINE")) : 0;
+  const int refine = scratch_ok ? refine_env : (refine_env & 1);
   int rc;
   rc = gemm_ws(LMN, LMN, EF_BETA | EF_LOWER, bw, bw, bw, 1.0, Lbb, ldl, Dbar, ldab, 0.0, nullptr, 0, P, bw,
                4, st);                                          // P = tril(L^T Lbar)
@@ -914,7 +924,11 @@ int potrf_bwd_hybrid_f64(const double* L, int ldl, double* Ab, int ldab, int n, 
 // triangle in Murray's convention (strict lower part = 2 x the symmetric gradient entry).
 int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int n, double* ws,
                             int ab_is_tril, int finalize, cudaStream_t st) {
-  const int m = bwd_block();
+  int m = bwd_block();
+  if (m > n) {                          // one block: round n up to the leaf granularity
+    m = pcfg::NB;
+    while (m < n) m *= 2;
+  }
   double* W = ws;                       // n x n, only the m x m diagonal blocks are non-zero
   double* S1 = W + (size_t)n * n;       // scratch: Cbar W_bb  /  P
   double* S2 = S1 + (size_t)n * n;      // scratch: T1  /  symmetrised block
@@ -1010,7 +1024,7 @@ int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int 
       leaf_rev_kernel<<<1, 256, pcfg::LEAF_SMEM, st>>>(L, ldl, Ab, ldab, s, bw);
       GPINV_CHECK_LAUNCH();
     } else {
-      rc = leaf_reverse_refined(Lbb, ldl, Wbb, n, Dbar, ldab, bw, S1, S2, S3, S4, st);
+      rc = leaf_reverse_refined(Lbb, ldl, Wbb, n, Dbar, ldab, bw, S1, S2, S3, S4, bw <= 2048, st);
       if (rc) return rc;
     }
     if (s > 0) {

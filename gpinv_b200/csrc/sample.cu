@@ -203,38 +203,56 @@ int sumsq_f64(const double* x, size_t count, double* out, cudaStream_t st) {
   return GPINV_OK;
 }
 
-// kl_out: device [4] = {KL, sumE2, sumU2, logdet}
-int sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q, int q_diag,
-                   const double* q_mu, const double* mean, const double* E, int n, int S, int R,
-                   double* U, double* F, double* expF, double* kl_out, cudaStream_t st) {
-  if (n <= 0 || S <= 0 || R <= 0) return GPINV_ERR_ARG;
-  if (!F && !expF) return GPINV_ERR_ARG;
+// U = q_mu + tril(Q) eps (GPinv/stvgp.py:162-168) and the partial sums of the stochastic KL
+// (GPinv/stvgp.py:160-161,170-172).  kl_out: device [4] = {KL, sumE2, sumU2, logdet}; KL itself is
+// written by kl_finish_f64 once sumU2 is complete.
+int sample_u_fwd_f64(const double* Q, int q_diag, const double* q_mu, const double* E, int n, int S, int R,
+                     double* U, double* kl_out, cudaStream_t st) {
   GPINV_TRY(cudaMemsetAsync(kl_out, 0, 4 * sizeof(double), st));
   const size_t sn = (size_t)S * n;
   sumsq_kernel<<<ew_grid((size_t)R * sn / 2 + 1), 256, 0, st>>>(E, (size_t)R * sn, kl_out + 1);
   GPINV_CHECK_LAUNCH();
   diag_logsq_kernel<<<min(cdiv(n * R, 256), 1024), 256, 0, st>>>(Q, n, R, q_diag, kl_out + 3);
   GPINV_CHECK_LAUNCH();
-  int rc;
   if (q_diag) {
     dim3 grid(ew_grid(sn), 1, R);
     udiag_fwd_kernel<<<grid, 256, 0, st>>>(Q, q_mu, E, n, S, U, kl_out + 2);
     GPINV_CHECK_LAUNCH();
+    return GPINV_OK;
   }
   for (int r = 0; r < R; ++r) {
-    if (!q_diag) {
-      GemmParams p = {};
-      p.A = E + r * sn; p.lda = n;
-      p.B = Q + (size_t)r * n * n; p.ldb = n;
-      p.M = S; p.N = n; p.K = n;
-      p.alpha = 1.0;
-      p.colvec = q_mu + (size_t)r * n;
-      p.out = U + r * sn; p.ldo = n;
-      p.sumsq = kl_out + 2;
-      p.kmode = 1; p.splitk = 1; p.allow_split = 1;
-      rc = gemm_launch(LK, LK, EF_COLVEC | EF_SUMSQ, p, st);
-      if (rc) return rc;
-    }
+    GemmParams p = {};
+    p.A = E + r * sn; p.lda = n;
+    p.B = Q + (size_t)r * n * n; p.ldb = n;
+    p.M = S; p.N = n; p.K = n;
+    p.alpha = 1.0;
+    p.colvec = q_mu + (size_t)r * n;
+    p.out = U + r * sn; p.ldo = n;
+    p.sumsq = kl_out + 2;
+    p.kmode = 1; p.splitk = 1; p.allow_split = 1;
+    const int rc = gemm_launch(LK, LK, EF_COLVEC | EF_SUMSQ, p, st);
+    if (rc) return rc;
+  }
+  return GPINV_OK;
+}
+
+int kl_finish_f64(double* kl_out, int S, cudaStream_t st) {
+  // parts layout for kl_finish: {sumE2, sumU2, logdet} = kl_out+1
+  kl_finish_kernel<<<1, 1, 0, st>>>(kl_out + 1, (double)S, kl_out);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
+// kl_out: device [4] = {KL, sumE2, sumU2, logdet}
+int sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q, int q_diag,
+                   const double* q_mu, const double* mean, const double* E, int n, int S, int R,
+                   double* U, double* F, double* expF, double* kl_out, cudaStream_t st) {
+  if (n <= 0 || S <= 0 || R <= 0) return GPINV_ERR_ARG;
+  if (!F && !expF) return GPINV_ERR_ARG;
+  int rc = sample_u_fwd_f64(Q, q_diag, q_mu, E, n, S, R, U, kl_out, st);
+  if (rc) return rc;
+  const size_t sn = (size_t)S * n;
+  for (int r = 0; r < R; ++r) {
     GemmParams p = {};
     p.A = U + r * sn; p.lda = n;
     p.B = Lc; p.ldb = ldl;
@@ -247,9 +265,52 @@ int sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
     rc = gemm_launch(LK, LK, expF ? (EF_COLVEC | EF_EXP2) : EF_COLVEC, p, st);
     if (rc) return rc;
   }
-  // parts layout for kl_finish: {sumE2, sumU2, logdet} = kl_out+1
-  kl_finish_kernel<<<1, 1, 0, st>>>(kl_out + 1, (double)S, kl_out);
+  return kl_finish_f64(kl_out, S, st);
+}
+
+int colsum_f64(const double* X, int n, int S, int R, double* out, cudaStream_t st) {
+  GPINV_TRY(cudaMemsetAsync(out, 0, (size_t)R * n * sizeof(double), st));
+  const int schunk = 64;
+  dim3 grid(cdiv(n, 256), cdiv(S, schunk), R);
+  colsum_kernel<<<grid, 256, 0, st>>>(X, n, S, schunk, out);
   GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
+// Tail of the reverse pass that does not depend on the form of the Cholesky factor: from Ubar to
+// qmu_bar (column sums, unless the caller's Ubar GEMM already produced them), Qbar = tril(Ubar^T E)
+// (or the diagonal version) and the d/dQ_ii term of the stochastic KL.
+int sample_q_bwd_f64(const double* Q, int q_diag, const double* E, const double* Ubar, const double* klbar,
+                     int n, int S, int R, double* qmu_bar, int qmu_from_colsum, double* Qbar, cudaStream_t st) {
+  const size_t sn = (size_t)S * n;
+  int rc;
+  if (qmu_from_colsum) {
+    rc = colsum_f64(Ubar, n, S, R, qmu_bar, st);
+    if (rc) return rc;
+  }
+  if (q_diag) {
+    GPINV_TRY(cudaMemsetAsync(Qbar, 0, (size_t)R * n * sizeof(double), st));
+    const int schunk = 64;
+    dim3 grid(cdiv(n, 256), cdiv(S, schunk), R);
+    udiag_bwd_kernel<<<grid, 256, 0, st>>>(Ubar, E, n, S, schunk, Qbar, nullptr);
+    GPINV_CHECK_LAUNCH();
+  } else {
+    for (int r = 0; r < R; ++r) {   // Qbar_r = tril(Ubar_r^T E_r)
+      GemmParams p = {};
+      p.A = Ubar + r * sn; p.lda = n;
+      p.B = E + r * sn; p.ldb = n;
+      p.M = n; p.N = n; p.K = S;
+      p.alpha = 1.0;
+      p.out = Qbar + (size_t)r * n * n; p.ldo = n;
+      p.kmode = 0; p.splitk = 1; p.allow_split = 1;
+      rc = gemm_launch(LMN, LMN, EF_LOWER, p, st);
+      if (rc) return rc;
+    }
+  }
+  if (klbar) {
+    diag_term_kernel<<<cdiv(n * R, 256), 256, 0, st>>>(Qbar, Q, n, R, q_diag, klbar, (double)S);
+    GPINV_CHECK_LAUNCH();
+  }
   return GPINV_OK;
 }
 
@@ -264,18 +325,11 @@ int sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
   if (n <= 0 || S <= 0 || R <= 0) return GPINV_ERR_ARG;
   const size_t sn = (size_t)S * n;
   GPINV_TRY(cudaMemsetAsync(qmu_bar, 0, (size_t)R * n * sizeof(double), st));
-  GPINV_TRY(cudaMemsetAsync(mean_bar, 0, (size_t)R * n * sizeof(double), st));
   GPINV_TRY(cudaMemsetAsync(svdot, 0, (size_t)R * sizeof(double), st));
-  if (q_diag) GPINV_TRY(cudaMemsetAsync(Qbar, 0, (size_t)R * n * sizeof(double), st));
-  const int schunk = 64;
-  {
-    dim3 grid(cdiv(n, 256), cdiv(S, schunk), R);
-    colsum_kernel<<<grid, 256, 0, st>>>(Fbar, n, S, schunk, mean_bar);
-    GPINV_CHECK_LAUNCH();
-  }
-  int rc;
+  int rc = colsum_f64(Fbar, n, S, R, mean_bar, st);
+  if (rc) return rc;
   for (int r = 0; r < R; ++r) {
-    {  // Ubar_r = sv_r Fbar_r Lc + klbar U_r ; qmu_bar (full) = colsum
+    {  // Ubar_r = sv_r Fbar_r Lc + klbar U_r ; qmu_bar = column sums (fused)
       GemmParams p = {};
       p.A = Fbar + r * sn; p.lda = n;
       p.B = Lc; p.ldb = ldl;
@@ -287,17 +341,6 @@ int sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
       p.colsum = qmu_bar + (size_t)r * n;
       p.kmode = 2; p.splitk = 1; p.allow_split = 1;
       rc = gemm_launch(LK, LMN, EF_BETA | EF_COLSUM, p, st);
-      if (rc) return rc;
-    }
-    if (!q_diag) {  // Qbar_r = tril(Ubar_r^T E_r)
-      GemmParams p = {};
-      p.A = Ubar + r * sn; p.lda = n;
-      p.B = E + r * sn; p.ldb = n;
-      p.M = n; p.N = n; p.K = S;
-      p.alpha = 1.0;
-      p.out = Qbar + (size_t)r * n * n; p.ldo = n;
-      p.kmode = 0; p.splitk = 1; p.allow_split = 1;
-      rc = gemm_launch(LMN, LMN, EF_LOWER, p, st);
       if (rc) return rc;
     }
     {  // Lc_bar (+)= sv_r tril(Fbar_r^T U_r) ; svdot_r = <that, Lc>
@@ -316,16 +359,7 @@ int sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double
       if (rc) return rc;
     }
   }
-  if (q_diag) {  // qbar[r][i] = sum_s Ubar E  (qmu_bar already came from the GEMM column sums)
-    dim3 grid(cdiv(n, 256), cdiv(S, schunk), R);
-    udiag_bwd_kernel<<<grid, 256, 0, st>>>(Ubar, E, n, S, schunk, Qbar, nullptr);
-    GPINV_CHECK_LAUNCH();
-  }
-  if (klbar) {
-    diag_term_kernel<<<cdiv(n * R, 256), 256, 0, st>>>(Qbar, Q, n, R, q_diag, klbar, (double)S);
-    GPINV_CHECK_LAUNCH();
-  }
-  return GPINV_OK;
+  return sample_q_bwd_f64(Q, q_diag, E, Ubar, klbar, n, S, R, qmu_bar, 0, Qbar, st);
 }
 
 int gauss_sumsq_f64(const double* F, const double* Y, int n, int S, int R, double* out,

@@ -124,6 +124,28 @@ int gpinv_sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const 
                          double* Qbar, double* Lc_bar, int ldlb, double* svdot, double* mean_bar,
                          void* stream);
 
+/* --- T6 kept factored: Kronecker core chol(K1) (x) chol(K2) of kronecker.RBF2D
+ * (GPinv/kronecker.py:10-22 kronecker_product, :49-66 RBF2D.Cholesky, which the reference multiplies
+ * out into a dense [n1 n2, n1 n2] matrix).  Row order i*n2 + j (testing/test_kronecker.py:37-41).
+ * gpinv_kron_apply_f64: F[b] = L1 U[b] L2^T (trans = 0, i.e. (L1 (x) L2) u) or L1^T U[b] L2 (trans = 1)
+ * for `batch` vectors stored as rows of U / F [batch, n1*n2]; T_ws [batch, n1*n2] scratch. */
+int gpinv_kron_apply_f64(const double* L1, int n1, const double* L2, int n2, const double* U, int batch,
+                         double* T_ws, double* F, int trans, void* stream);
+/* Sampling stage of GPinv/stvgp.py:144-185 with that factored core: same contract as
+ * gpinv_sample_fwd_f64 / gpinv_sample_bwd_f64 with Lc replaced by (L1 [n1,n1], L2 [n2,n2]), n = n1*n2.
+ * T [R,S,n] (= U L2^T per sample) is an extra output kept for the reverse, which returns L1bar
+ * [n1,n1] and L2bar [n2,n2] (lower triangles) and svdot [R] = dObj/d sqrt(variance_r). */
+int gpinv_kron_sample_fwd_f64(const double* L1, int n1, const double* L2, int n2, const double* sqrt_v,
+                              const double* Q, int q_diag, const double* q_mu, const double* mean,
+                              const double* E, int S, int R, double* U, double* T, double* F, double* expF,
+                              double* kl_out, void* stream);
+size_t gpinv_kron_bwd_ws_bytes(int n1, int n2, int S, int R);
+int gpinv_kron_sample_bwd_f64(const double* L1, int n1, const double* L2, int n2, const double* sqrt_v,
+                              const double* Q, int q_diag, const double* E, const double* U, const double* T,
+                              const double* Fbar, const double* klbar, int S, int R, double* Ubar,
+                              double* qmu_bar, double* Qbar, double* L1bar, double* L2bar, double* svdot,
+                              double* mean_bar, void* ws, void* stream);
+
 /* --- T14: Gaussian likelihood (GPinv/likelihoods.py:70-76): sum (F - Y)^2 over [R,S,n] with
  * Y [n,R]; reverse Fbar = coef (Y - F), coef a device scalar. */
 int gpinv_gauss_sumsq_f64(const double* F, const double* Y, int n, int S, int R, double* out,
