@@ -42,6 +42,8 @@ SIGNATURES = {
     "gpinv_chol_core_bwd_f64": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
     "gpinv_trsm_rlt_f64": (_I, [_P, _I, _P, _I, _I, _I, _P]),
     "gpinv_gemm_f64": (_I, [_I, _I, _I, _I, _I, _D, _P, _I, _P, _I, _D, _P, _I, _I, _P]),
+    "gpinv_gemm_ex_f64": (_I, [_I, _I, _I, _I, _I, _D, _P, _I, C.c_longlong, _P, _I, C.c_longlong, _D, _P, _I,
+                               C.c_longlong, _I, _I, _I, _I, _P]),
     "gpinv_tril_unpack_f64": (_I, [_P, _P, _I, _I, _P]),
     "gpinv_tril_pack_f64": (_I, [_P, _P, _I, _I, _P]),
     "gpinv_sample_fwd_f64": (_I, [_P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -251,6 +251,19 @@ int gpinv_gemm_f64(int transa, int transb, int m, int n, int k, double alpha, co
   return gemm_launch(la, lb, EF_BETA | (lower ? EF_LOWER : 0u), p, ST(stream));
 }
 
+// Test / bring-up entry: the DMMA GEMM with every knob of the library-internal launcher exposed
+// (layouts, triangular k-range mode, lower output, batching, stream-K permission).
+int gpinv_gemm_ex_f64(int la, int lb, int m, int n, int k, double alpha, const double* A, int lda,
+                      long long strideA, const double* B, int ldb, long long strideB, double beta, double* C,
+                      int ldc, long long strideC, int batch, int lower, int kmode, int allow_split, void* stream) {
+  GemmParams p = {};
+  p.A = A; p.B = B; p.M = m; p.N = n; p.K = k; p.lda = lda; p.ldb = ldb;
+  p.alpha = alpha; p.beta = beta; p.Cin = C; p.ldcin = ldc; p.out = C; p.ldo = ldc;
+  p.kmode = kmode; p.splitk = 1; p.allow_split = allow_split;
+  p.batch = batch; p.strideA = strideA; p.strideB = strideB; p.strideO = strideC; p.strideCin = strideC;
+  return gemm_launch(la, lb, EF_BETA | (lower ? EF_LOWER : 0u), p, ST(stream));
+}
+
 int gpinv_tril_unpack_f64(const double* src, double* dst, int n, int R, void* stream) {
   return tril_unpack_f64(src, dst, n, R, ST(stream));
 }

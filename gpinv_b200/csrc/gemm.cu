@@ -338,7 +338,7 @@ int gemm_simple(int la, int lb, int M, int N, int K, double alpha, const double*
 int gemm_batched(int la, int lb, int M, int N, int K, double alpha, const double* A, int lda,
                  long long strideA, const double* B, int ldb, long long strideB, double beta,
                  double* C, int ldc, long long strideC, int batch, bool lower, int kmode,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, int allow_split, int ws_slot) {
   if (batch <= 0) return GPINV_OK;
   GemmParams p = {};
   p.A = A; p.B = B; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb;
@@ -346,6 +346,7 @@ int gemm_batched(int la, int lb, int M, int N, int K, double alpha, const double
   p.kmode = kmode; p.splitk = 1;
   p.batch = batch; p.strideA = strideA; p.strideB = strideB; p.strideO = strideC;
   p.strideCin = strideC;
+  p.allow_split = allow_split; p.ws_slot = ws_slot;
   unsigned ef = EF_BETA;
   if (lower) ef |= EF_LOWER;
   return gemm_launch(la, lb, ef, p, stream);

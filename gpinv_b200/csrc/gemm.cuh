@@ -555,6 +555,6 @@ int gemm_simple(int la, int lb, int M, int N, int K, double alpha, const double*
 int gemm_batched(int la, int lb, int M, int N, int K, double alpha, const double* A, int lda,
                  long long strideA, const double* B, int ldb, long long strideB, double beta,
                  double* C, int ldc, long long strideC, int batch, bool lower, int kmode,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int allow_split = 0, int ws_slot = 0);
 
 }  // namespace gpinv

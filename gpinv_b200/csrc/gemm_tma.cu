@@ -275,7 +275,8 @@ constexpr int TMA_CNT_SLOTS = 16384;     // must equal CNT_SLOTS in gemm.cu
 bool gemm_tma_try_launch(int la, int lb, unsigned ef, GemmParams& p, bool small, cudaStream_t stream, int* rc) {
   static const bool disabled = (getenv("GPINV_GEMM_LEGACY") != nullptr);
   if (disabled || small) return false;     // 64x64-tile problems: cp.async kernels (see gemm_tma.cuh)
-  // TMA needs 16-byte aligned bases and strides; anything else stays on the cp.async path
+  // TMA needs 16-byte aligned bases and strides; anything else stays on the cp.async path.  Ragged
+  // M / N / K are fine: out-of-bounds parts of a box are zero-filled by the hardware.
   if (!aligned16(p.A) || !aligned16(p.B) || (p.lda & 1) || (p.ldb & 1)) return false;
   if (p.batch > 1 && ((p.strideA & 1) || (p.strideB & 1))) return false;
   if (p.splitk > 1) return false;          // caller-imposed atomic split: legacy semantics

@@ -64,11 +64,8 @@ struct TmaCfg {
 // 384 threads start with 168 registers; the DMMA warps take 232, the producer warpgroup keeps 40
 using TmaBig = TmaCfg<8, 4, 2, 4, 6, 1, 232, 40>;
 // 64x64 tile, 4 DMMA warps (warp tile 32x32) + producer warpgroup, 4 stages x 16 KB, 3 CTAs/SM.
-// NOT INSTANTIATED: with three co-resident CTAs per SM (shared memory and register file both nearly
-// full, setmaxnreg in every CTA) the third CTA of an SM returned wrong partial sums on B200 for
-// strided operand windows (tests/gpu_gemm_inplace.py); the same code with 3 stages, or without
-// setmaxnreg, or at 2 CTAs/SM, passes, and no protocol race was found.  Small / short-K problems
-// therefore stay on the cp.async kernels of gemm.cuh (3 CTAs/SM, no register re-allocation).
+// Not instantiated: small / short-K problems (a few k-tiles per tile) gain nothing from the ring and
+// measured slower than the cp.async kernels of gemm.cuh (1024^3: 9.9 vs 16.9 TF/s), which keep them.
 using TmaSmall = TmaCfg<4, 4, 2, 2, 4, 3, 136, 24>;
 
 // ------------------------------------ PTX wrappers ------------------------------------
@@ -416,6 +413,14 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
+      // Release the stage only after this warp's fragment loads have been PERFORMED.  ptxas schedules
+      // the arrive right behind the ISSUE of the last LDS (it has no register dependence on the loaded
+      // values), and on B200 the SYNCS arrive can take effect while that LDS is still queued: the
+      // producer, blocked on this barrier, then refills the stage under the load and the tile gets a
+      // wrong partial sum -- sporadically (tests/gpu_gemm_chain.py: up to 39 of 40 repetitions at ragged
+      // sizes, 1 of 59 at aligned ones).  A CTA-scope fence orders the loads before the arrive; it
+      // costs ~40 cycles per 4096-cycle k-tile.
+      __threadfence_block();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }

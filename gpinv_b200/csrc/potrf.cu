@@ -730,7 +730,7 @@ __global__ void mirror_lower_kernel(double* __restrict__ A, int n, int ld) {
 // With `stop` < n only the diagonal blocks of size `stop` (a power-of-two multiple of NB, blocks
 // aligned at multiples of `stop`) are inverted; the rest of W stays zero.
 static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cudaStream_t st,
-                     int stop = 0x7fffffff) {
+                     int stop = 0x7fffffff, int ws_slot = 0) {
   using namespace pcfg;
   static bool attr = false;
   const int smem = (NB * LDT + NB + NB * LDR) * 8;
@@ -757,12 +757,12 @@ static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cuda
       // T21 = L21 W11   (W11 lower: B(c,k) = W11[k][c] is zero for k < c)
       rc = gemm_batched(LK, LMN, rows, s, s, 1.0, L + (size_t)m0 * ldl + i0, ldl, strL,
                         W + (size_t)i0 * n + i0, n, strW, 0.0, T + (size_t)m0 * n + i0, n, strW,
-                        batch, false, 2, st);
+                        batch, false, 2, st, 1, ws_slot);
       if (rc) return rc;
       // W21 = -W22 T21  (W22 lower: A(r,k) zero for k > r)
       rc = gemm_batched(LK, LMN, rows, s, rows, -1.0, W + (size_t)m0 * n + m0, n, strW,
                         T + (size_t)m0 * n + i0, n, strW, 0.0, W + (size_t)m0 * n + i0, n, strW,
-                        batch, false, 3, st);
+                        batch, false, 3, st, 1, ws_slot);
       if (rc) return rc;
     }
   }

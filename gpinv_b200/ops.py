@@ -364,6 +364,97 @@ stvgp_sample.register_autograd(_sample_backward, setup_context=_sample_setup)
 
 
 # --------------------------------------------------------------------------------------
+# T6 + T8-T13 with the Kronecker core kept factored (kronecker.RBF2D)
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("gpinv::kron_apply", mutates_args=(), device_types="cuda")
+def kron_apply(L1: Tensor, L2: Tensor, U: Tensor, trans: bool) -> Tensor:
+    """F[b] = L1 U[b] L2^T (trans False: (L1 (x) L2) u, GPinv/kronecker.py:10-22 applied without forming
+    the product) or L1^T U[b] L2 (trans True) for the rows of U [B, n1*n2]."""
+    L1 = _chk(L1, "L1"); L2 = _chk(L2, "L2"); U = _chk(U, "U")
+    n1, n2 = L1.shape[0], L2.shape[0]
+    B = U.shape[0]
+    T = torch.empty_like(U)
+    F = torch.empty_like(U)
+    rc = _capi.lib().gpinv_kron_apply_f64(_p(L1), n1, _p(L2), n2, _p(U), B, _p(T), _p(F), int(trans), _st())
+    _capi.check(rc, "kron_apply")
+    return F
+
+
+@torch.library.custom_op("gpinv::kron_sample", mutates_args=(), device_types="cuda")
+def kron_sample(L1: Tensor, L2: Tensor, sqrt_v: Tensor, Q: Tensor, q_mu: Tensor, mean: Tensor, E: Tensor,
+                q_diag: bool, want_exp: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """(F [R,S,n], expF or empty, KL [1], U [R,S,n], T [R,S,n]) with the Cholesky factor
+    sqrt_v_r * (L1 (x) L2) of kronecker.RBF2D kept factored (GPinv/kronecker.py:49-66 feeding
+    GPinv/stvgp.py:144-185).  Q [R,n,n] lower or [R,n] (q_diag)."""
+    L1 = _chk(L1, "L1"); L2 = _chk(L2, "L2"); sqrt_v = _chk(sqrt_v, "sqrt_v"); Q = _chk(Q, "Q")
+    q_mu = _chk(q_mu, "q_mu"); mean = _chk(mean, "mean"); E = _chk(E, "E")
+    ensure_workspace(E.device)
+    R, S, n = E.shape
+    n1, n2 = L1.shape[0], L2.shape[0]
+    assert n1 * n2 == n
+    U = torch.empty_like(E)
+    T = torch.empty_like(E)
+    F = torch.empty_like(E)
+    expF = torch.empty_like(E) if want_exp else torch.empty(0, dtype=torch.float64, device=E.device)
+    kl = torch.empty(4, dtype=torch.float64, device=E.device)
+    rc = _capi.lib().gpinv_kron_sample_fwd_f64(_p(L1), n1, _p(L2), n2, _p(sqrt_v), _p(Q), int(q_diag), _p(q_mu),
+                                               _p(mean), _p(E), S, R, _p(U), _p(T), _p(F),
+                                               _p(expF) if want_exp else None, _p(kl), _st())
+    _capi.check(rc, "kron_sample_fwd")
+    return F, expF, kl[:1].clone(), U, T
+
+
+@torch.library.custom_op("gpinv::kron_sample_bwd", mutates_args=(), device_types="cuda")
+def kron_sample_bwd(L1: Tensor, L2: Tensor, sqrt_v: Tensor, Q: Tensor, E: Tensor, U: Tensor, T: Tensor,
+                    Fbar: Tensor, klbar: Optional[Tensor], q_diag: bool) -> List[Tensor]:
+    """[L1bar, L2bar, sqrt_v_bar, Qbar, qmu_bar, mean_bar]."""
+    L1 = _chk(L1, "L1"); L2 = _chk(L2, "L2"); sqrt_v = _chk(sqrt_v, "sqrt_v"); Q = _chk(Q, "Q")
+    E = _chk(E, "E"); U = _chk(U, "U"); T = _chk(T, "T"); Fbar = _chk(Fbar, "Fbar")
+    ensure_workspace(E.device)
+    if klbar is not None:
+        klbar = _chk(klbar, "klbar")
+    R, S, n = E.shape
+    n1, n2 = L1.shape[0], L2.shape[0]
+    dev = E.device
+    Ubar = torch.empty_like(E)
+    qmu_bar = torch.empty((R, n), dtype=torch.float64, device=dev)
+    Qbar = torch.empty_like(Q)
+    L1bar = torch.empty((n1, n1), dtype=torch.float64, device=dev)
+    L2bar = torch.zeros((n2, n2), dtype=torch.float64, device=dev)
+    svbar = torch.empty(R, dtype=torch.float64, device=dev)
+    mean_bar = torch.empty((R, n), dtype=torch.float64, device=dev)
+    lib = _capi.lib()
+    ws = _ws(lib.gpinv_kron_bwd_ws_bytes(n1, n2, S, R), E)
+    rc = lib.gpinv_kron_sample_bwd_f64(_p(L1), n1, _p(L2), n2, _p(sqrt_v), _p(Q), int(q_diag), _p(E), _p(U), _p(T),
+                                       _p(Fbar), _p(klbar), S, R, _p(Ubar), _p(qmu_bar), _p(Qbar), _p(L1bar),
+                                       _p(L2bar), _p(svbar), _p(mean_bar), _p(ws), _st())
+    _capi.check(rc, "kron_sample_bwd")
+    return [L1bar, L2bar, svbar, Qbar, qmu_bar, mean_bar]
+
+
+def _kron_setup(ctx, inputs, output):
+    L1, L2, sqrt_v, Q, q_mu, mean, E, q_diag, want_exp = inputs
+    F, expF, kl, U, T = output
+    ctx.save_for_backward(L1, L2, sqrt_v, Q, E, U, T, expF)
+    ctx.q_diag = q_diag
+    ctx.want_exp = want_exp
+
+
+def _kron_backward(ctx, Fbar, expFbar, klbar, Ubar_unused, Tbar_unused):
+    L1, L2, sqrt_v, Q, E, U, T, expF = ctx.saved_tensors
+    if Fbar is None:
+        Fbar = torch.zeros_like(E)
+    if ctx.want_exp and expFbar is not None:
+        Fbar = Fbar + expFbar * expF
+    L1bar, L2bar, sv_bar, Qbar, qmu_bar, mean_bar = kron_sample_bwd(
+        L1, L2, sqrt_v, Q, E, U, T, Fbar.contiguous(), None if klbar is None else klbar.contiguous(), ctx.q_diag)
+    return L1bar, L2bar, sv_bar, Qbar, qmu_bar, mean_bar, None, None, None
+
+
+kron_sample.register_autograd(_kron_backward, setup_context=_kron_setup)
+
+
+# --------------------------------------------------------------------------------------
 # T14 Gaussian likelihood on latent samples
 # --------------------------------------------------------------------------------------
 LOG2PI = 1.8378770664093453

@@ -101,6 +101,13 @@ int gpinv_gemm_f64(int transa, int transb, int m, int n, int k, double alpha, co
                    int lda, const double* B, int ldb, double beta, double* C, int ldc, int lower,
                    void* stream);
 
+/* Bring-up / test entry: the same GEMM with the launcher's knobs exposed.  la / lb: 0 = element (r,k)
+ * at p[r*ld + k], 1 = at p[k*ld + r]; kmode: triangular k-range skipping (0 none, 1: k < n0+BN,
+ * 2: k >= n0, 3: k < m0+BM, 4: k >= m0, 5: both 2 and 3); batch problems `stride*` elements apart. */
+int gpinv_gemm_ex_f64(int la, int lb, int m, int n, int k, double alpha, const double* A, int lda,
+                      long long strideA, const double* B, int ldb, long long strideB, double beta, double* C,
+                      int ldc, long long strideC, int batch, int lower, int kmode, int allow_split, void* stream);
+
 /* --- T7: tril(q_sqrt) with the reference's [n,n,R] -> [R,n,n] transpose
  * (GPinv/stvgp.py:156-157) and its reverse. */
 int gpinv_tril_unpack_f64(const double* q_sqrt_nnR, double* Q_Rnn, int n, int R, void* stream);

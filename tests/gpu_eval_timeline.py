@@ -25,8 +25,8 @@ if os.environ.get("GPINV_TIMELINE_CHILD") != "1":
         f.write("# start_us  dur_us  [TF/s executed]  kernel | gemm geometry (launch order)\n")
         for st, du, nm in rows:
             extra = ""
-            if "gemm_dmma" in nm and gi < len(logs):
-                g = dict(kv.split("=") for kv in logs[gi].split()[1:])
+            if ("gemm_dmma" in nm or "gemm_tma" in nm) and gi < len(logs):
+                g = dict(kv.split("=") for kv in logs[gi].split()[1:] if "=" in kv)
                 gi += 1
                 Mm, Nn, Kk, b = int(g["M"]), int(g["N"]), int(g["K"]), int(g["batch"])
                 ef, km = int(g["ef"]), int(g["kmode"])

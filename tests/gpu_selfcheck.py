@@ -227,9 +227,57 @@ def check_liks():
     report("sumsq", rel(ops.sumsq(t(x)), torch.tensor([np.sum(x * x)])), 1e-13)
 
 
+def check_kron():
+    """Kronecker-factored apply and sampling stage against the dense Kronecker product."""
+    rng = np.random.RandomState(5)
+    for (n1, n2, B) in [(3, 5, 4), (6, 9, 7), (64, 128, 33), (70, 50, 130)]:
+        L1 = np.tril(rng.randn(n1, n1)) + 2 * np.eye(n1)
+        L2 = np.tril(rng.randn(n2, n2)) + 2 * np.eye(n2)
+        U = rng.randn(B, n1 * n2)
+        dense = np.kron(L1, L2)
+        for trans in (False, True):
+            ref = U @ (dense if trans else dense.T)
+            out = ops.kron_apply(t(L1), t(L2), t(U), trans)
+            report("kron_apply %dx%d B=%d trans=%d" % (n1, n2, B, trans), rel(out, torch.tensor(ref)), 1e-13)
+    for (n1, n2, S, R, q_diag, want_exp) in [(4, 5, 6, 2, True, False), (6, 9, 7, 3, False, False), (12, 20, 16, 3, False, True),
+                                             (16, 24, 40, 2, True, True), (64, 40, 33, 1, False, False)]:
+        n = n1 * n2
+        L1 = np.tril(0.3 * rng.randn(n1, n1)) + np.eye(n1)
+        L2 = np.tril(0.3 * rng.randn(n2, n2)) + np.eye(n2)
+        sv = np.exp(0.2 * rng.randn(R))
+        q_mu, mean, E = 0.3 * rng.randn(n, R), 0.2 * rng.randn(n, R), rng.randn(R, S, n)
+        q_sqrt = np.exp(0.3 * rng.randn(n, R)) if q_diag else 0.5 * np.eye(n)[:, :, None] + 0.1 * rng.randn(n, n, R)
+        tl = [torch.tensor(a, requires_grad=True) for a in (L1, L2, sv, q_sqrt, q_mu, mean)]
+        L1t, L2t, svt, qst, qmt, mnt = tl
+        Lfull = O.kronecker_product(torch.tril(L1t), torch.tril(L2t))[:, :, None] * svt[None, None, :]
+        f, KL = O.stvgp_sample(qmt, qst, Lfull, mnt, torch.tensor(E), q_diag)
+        Wf = torch.tensor(rng.randn(S, n, R))
+        obj = ((torch.exp(0.1 * f) if want_exp else f) * Wf).sum() - 0.37 * KL
+        gref = torch.autograd.grad(obj, tl)
+        dl = [t(a).requires_grad_(True) for a in (L1, L2, sv, q_sqrt, q_mu, mean)]
+        L1d, L2d, svd, qsd, qmd, mnd = dl
+        Q = qsd.T.contiguous() if q_diag else ops.tril_unpack(qsd)
+        F, expF, kl, U, T = ops.kron_sample(L1d, L2d, svd, Q, qmd.T.contiguous(), mnd.T.contiguous(), t(E), q_diag, want_exp)
+        fd = F.permute(1, 2, 0)
+        tag = "kron_sample %dx%d S=%d R=%d diag=%d exp=%d" % (n1, n2, S, R, q_diag, want_exp)
+        report(tag + " F", rel(fd, f), 1e-12)
+        report(tag + " KL", rel(kl, KL.reshape(1)), 1e-12)
+        if want_exp:
+            report(tag + " expF", rel(expF.permute(1, 2, 0), torch.exp(f)), 1e-12)
+        objd = ((torch.exp(0.1 * fd) if want_exp else fd) * Wf.to(dev)).sum() - 0.37 * kl.sum()
+        gout = torch.autograd.grad(objd, dl)
+        for nm, a, b in zip(("L1", "L2", "sqrt_v", "q_sqrt", "q_mu", "mean"), gout, gref):
+            if nm in ("L1", "L2"):
+                a, b = torch.tril(a), torch.tril(b)
+            if nm == "q_sqrt" and not q_diag:
+                a, b = torch.tril(a.permute(2, 0, 1)), torch.tril(b.permute(2, 0, 1))
+            report(tag + " d/d" + nm, rel(a, b), 1e-11)
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    names = sys.argv[1:] or ["check_gemm", "check_kcore", "check_potrf", "check_trsm", "check_sample", "check_liks"]
+    names = sys.argv[1:] or ["check_gemm", "check_kcore", "check_potrf", "check_trsm", "check_sample", "check_kron",
+                             "check_liks"]
     for fn in [globals()[nm] for nm in names]:
         try:
             fn()
