@@ -250,7 +250,7 @@ def roofline_section(m, x, eps, n, M, S, world, t_eval, args, dev):
     t_ours = _time_events(lambda: ops.potrf(Kc), 5)
     Xr = m.X.tensor().contiguous()
     ls = torch.full((1,), 0.3, dtype=torch.float64, device=dev)
-    t_chol_core = _time_events(lambda: ops.chol_core(Xr, ls, 1, 1e-6), 5)
+    t_chol_core = _time_events(lambda: ops.chol_core(Xr, ls, 1, 1e-6, False), 5)
     denominators = {
         "cublas_dgemm_8192_burst_tflops": burst, "cublas_dgemm_8192_sustained_4s_tflops": sustained,
         "cusolver_potrf_4096_ms": 1e3 * t_cusolver, "cusolver_potrf_4096_tflops": 4096 ** 3 / 3 / t_cusolver / 1e12,

@@ -28,7 +28,11 @@ size_t potrf_bwd_inv_ws_bytes(int);
 int potrf_bwd_inv_f64(const double*, int, double*, int, int, double*, cudaStream_t);
 int potrf_bwd_hybrid_f64(const double*, int, double*, int, int, double*, cudaStream_t);
 int potrf_bwd_hybrid_block();
-int potrf_bwd_hybrid_ex_f64(const double*, int, double*, int, int, double*, int, int, cudaStream_t);
+int potrf_bwd_hybrid_ex_f64(const double*, int, double*, int, int, double*, int, int, cudaStream_t,
+                            const double* W_pre = nullptr);
+int trtri_side_f64(const double*, int, double*, double*, int, cudaStream_t);
+int trtri_side_join_f64(cudaStream_t);
+int trtri_side_sync_f64();
 int potrf_ex_f64(double*, int, int, int*, int, cudaStream_t);
 int tril_copy_f64(const double*, int, double*, int, int, cudaStream_t);
 int kbuild_ex_f64(const double*, const double*, int, int, int, int, int, const double*, int, int, double,
@@ -214,6 +218,14 @@ int gpinv_chol_core_f64(const double* X, int n, int D, int ldx, const double* ls
   return potrf_ex_f64(L, n, ldl, info, 1, ST(stream));
 }
 
+int gpinv_trtri_side_f64(const double* L, int ldl, double* Winv, double* scratch, int n, void* stream) {
+  if (n <= 0 || ldl < n || !Winv || !scratch) return GPINV_ERR_ARG;
+  return trtri_side_f64(L, ldl, Winv, scratch, n, ST(stream));
+}
+
+int gpinv_trtri_side_join(void* stream) { return trtri_side_join_f64(ST(stream)); }
+int gpinv_trtri_side_sync(void) { return trtri_side_sync_f64(); }
+
 size_t gpinv_chol_core_bwd_ws_bytes(int n, int D) {
   return (size_t)n * n * sizeof(double) + potrf_bwd_inv_ws_bytes(n) + kbuild_ws_bytes(n, n, D);
 }
@@ -221,13 +233,23 @@ size_t gpinv_chol_core_bwd_ws_bytes(int n, int D) {
 int gpinv_chol_core_bwd_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
                             int mode, const double* L, int ldl, const double* Lbar, int ldlb,
                             double* ls_bar, void* ws, void* stream) {
+  return gpinv_chol_core_bwd2_f64(X, n, D, ldx, ls, ard, mode, L, ldl, Lbar, ldlb, nullptr, ls_bar, ws, stream);
+}
+
+int gpinv_chol_core_bwd2_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
+                             int mode, const double* L, int ldl, const double* Lbar, int ldlb,
+                             const double* Winv, double* ls_bar, void* ws, void* stream) {
   if (n <= 0 || D <= 0 || ldl < n || ldlb < n) return GPINV_ERR_ARG;
   double* Ab = static_cast<double*>(ws);              // n x n: tril(Lbar), then the Murray-lower Kbar
   double* sweep_ws = Ab + (size_t)n * n;              // potrf_bwd_inv_ws_bytes(n)
   double* kws = sweep_ws + potrf_bwd_inv_ws_bytes(n) / sizeof(double);
   int rc = tril_copy_f64(Lbar, ldlb, Ab, n, n, ST(stream));
   if (rc) return rc;
-  rc = potrf_bwd_hybrid_ex_f64(L, ldl, Ab, n, n, sweep_ws, 1, 0, ST(stream));
+  if (Winv) {
+    rc = trtri_side_join_f64(ST(stream));
+    if (rc) return rc;
+  }
+  rc = potrf_bwd_hybrid_ex_f64(L, ldl, Ab, n, n, sweep_ws, 1, 0, ST(stream), Winv);
   if (rc) return rc;
   return kbuild_bwd_ex_f64(X, nullptr, n, n, D, ldx, ldx, ls, ard, mode, Ab, n, ls_bar, kws, 1, ST(stream));
 }

@@ -164,26 +164,30 @@ const SchedEntry* get_sched(const GemmParams& p, bool lower, bool small, bool at
   const double mk_whole = whole_partition(G0, st_whole);
   const double ideal_whole = (double)(W + (long long)fixed * T) / gmax;
 
-  // (2) stream-K: equal unit counts, cuts snapped away from tile boundaries' immediate neighbourhood
+  // (2) stream-K: equal COST per CTA, where a tile costs its k-tiles plus the fixed prologue / epilogue
+  // (a CTA whose range is made of many short tiles -- the tail of a triangular product -- would
+  // otherwise carry up to 40 % more than its share); cuts are snapped away from tile boundaries
   bool use_split = false;
   std::vector<unsigned> st_split;
   int Gs = 0;
   if ((key.allow_split || atomic) && W >= 16) {
     const int min_units = small ? 12 : 8;
+    const long long Wf = W + (long long)fixed * T;
     Gs = (int)((W / min_units) < gmax ? (W / min_units) : gmax);
     if (Gs > 24 * T) Gs = (int)(24 * T);     // the last arriver sums the slices serially: bound their number
     if (Gs < 1) Gs = 1;
-    const double mk_split = (double)(W + (long long)fixed * T) / Gs + fixed + (atomic ? 0 : 4);
+    const double mk_split = (double)Wf / Gs + fixed + (atomic ? 0 : 4);
     if (Gs > 1 && mk_split < 0.93 * mk_whole) {
       st_split.assign(Gs + 1, 0);
-      long long i = 0, before = 0;       // tile i starts at unit offset `before`
+      long long i = 0, before = 0;       // tile i starts at cost offset `before`
       for (int c = 1; c < Gs; ++c) {
-        const long long target = W * c / Gs;
-        while (i < T && before + units[(size_t)i] <= target) { before += units[(size_t)i]; ++i; }
-        long long koff = target - before;
+        const long long target = Wf * c / Gs;
+        while (i < T && before + units[(size_t)i] + fixed <= target) { before += units[(size_t)i] + fixed; ++i; }
+        // inside tile i: the first `fixed` cost units are its prologue, the rest its k-tiles
+        long long koff = target - before - fixed / 2;
         const int kt = (i < T) ? kts[(size_t)i] : 0;
         if (koff < 3 || kt == 0) koff = 0;                 // snap to the tile's start
-        else if (kt - koff < 3) { before += units[(size_t)i]; ++i; koff = 0; }   // ... or to its end
+        else if (kt - koff < 3) { before += units[(size_t)i] + fixed; ++i; koff = 0; }   // ... or to its end
         unsigned pos = ((unsigned)i << 16) | (unsigned)koff;
         if (pos < st_split[c - 1]) pos = st_split[c - 1];
         st_split[c] = pos;

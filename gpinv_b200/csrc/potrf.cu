@@ -399,6 +399,7 @@ static int pick_splitk(int M, int N, int K, bool lower) {
 struct LookAhead {
   cudaStream_t side = nullptr;
   cudaEvent_t evP = nullptr, evB = nullptr;
+  cudaEvent_t evF = nullptr, evW = nullptr;    // forward factor ready / explicit inverse ready (see trtri_side_f64)
   bool ok = false;
 };
 static LookAhead* lookahead_for_current_device() {
@@ -410,6 +411,8 @@ static LookAhead* lookahead_for_current_device() {
     if (cudaStreamCreateWithFlags(&la.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&la.evP, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&la.evB, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&la.evF, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&la.evW, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     la.ok = true;
   }
   return &la;
@@ -862,7 +865,7 @@ static int bwd_block() {
 }
 
 int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int n, double* ws,
-                            int ab_is_tril, int finalize, cudaStream_t st);
+                            int ab_is_tril, int finalize, cudaStream_t st, const double* W_pre = nullptr);
 
 // Reverse of ONE diagonal block by the inverse formula, with both triangular solves refined:
 //   G = sym(L^-T Phi(L^T Lbar) L^-1),   W ~ L^-1 explicit.
@@ -923,22 +926,24 @@ int potrf_bwd_hybrid_f64(const double* L, int ldl, double* Ab, int ldab, int n, 
 // ab_is_tril: Ab already has a zero strict upper part.  finalize = 0 leaves the result as a lower
 // triangle in Murray's convention (strict lower part = 2 x the symmetric gradient entry).
 int potrf_bwd_hybrid_ex_f64(const double* L, int ldl, double* Ab, int ldab, int n, double* ws,
-                            int ab_is_tril, int finalize, cudaStream_t st) {
+                            int ab_is_tril, int finalize, cudaStream_t st, const double* W_pre) {
   int m = bwd_block();
   if (m > n) {                          // one block: round n up to the leaf granularity
     m = pcfg::NB;
     while (m < n) m *= 2;
   }
-  double* W = ws;                       // n x n, only the m x m diagonal blocks are non-zero
-  double* S1 = W + (size_t)n * n;       // scratch: Cbar W_bb  /  P
+  double* Wown = ws;                    // n x n, only the m x m diagonal blocks are non-zero
+  const double* W = W_pre ? W_pre : Wown;   // W_pre: whole inverse already built (trtri_side_f64)
+  double* S1 = Wown + (size_t)n * n;    // scratch: Cbar W_bb  /  P
   double* S2 = S1 + (size_t)n * n;      // scratch: T1  /  symmetrised block
   double* S3 = S2 + (size_t)n * n;      // scratch of the refined diagonal-block reverse (m x m each)
   double* S4 = S3 + (size_t)m * m;
   int rc = GPINV_OK;
-  if (n > pcfg::NB) {     // (a single 64-wide block is reversed by substitution: no inverse needed)
-    GPINV_TRY(cudaMemsetAsync(W, 0, (size_t)n * n * sizeof(double), st));
-    rc = trtri_f64(L, ldl, W, S1, n, st, m);
+  if (n > pcfg::NB && !(W_pre && m >= n)) {     // (a single 64-wide block is reversed by substitution)
+    GPINV_TRY(cudaMemsetAsync(Wown, 0, (size_t)n * n * sizeof(double), st));
+    rc = trtri_f64(L, ldl, Wown, S1, n, st, m);
     if (rc) return rc;
+    W = Wown;
   }
   dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n, 8));
   if (!ab_is_tril) {
@@ -1063,6 +1068,37 @@ int tril_copy_f64(const double* src, int lds, double* dst, int ldd, int n, cudaS
 }
 
 int potrf_bwd_hybrid_block() { return bwd_block(); }
+
+// W <- L^-1 (n x n, ld n) on the library's side stream, started as soon as everything enqueued on `st`
+// so far (the factorisation) is done.  The inverse only depends on L, so it overlaps the sampling /
+// likelihood stages that follow on `st`; trtri_side_join_f64 makes a stream wait for it (the reverse
+// sweep calls it before its first use of W).  T: n x n scratch.  Split-K workspace half 1.
+int trtri_side_f64(const double* L, int ldl, double* W, double* T, int n, cudaStream_t st) {
+  LookAhead* la = lookahead_for_current_device();
+  if (!la) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaEventRecord(la->evF, st));
+  GPINV_TRY(cudaStreamWaitEvent(la->side, la->evF, 0));
+  GPINV_TRY(cudaMemsetAsync(W, 0, (size_t)n * n * sizeof(double), la->side));
+  int rc = trtri_f64(L, ldl, W, T, n, la->side, 0x7fffffff, 1);
+  if (rc) return rc;
+  GPINV_TRY(cudaEventRecord(la->evW, la->side));
+  return GPINV_OK;
+}
+
+// host-side wait for the side stream (used when an inverse buffer is about to be recycled)
+int trtri_side_sync_f64() {
+  LookAhead* la = lookahead_for_current_device();
+  if (!la) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaStreamSynchronize(la->side));
+  return GPINV_OK;
+}
+
+int trtri_side_join_f64(cudaStream_t st) {
+  LookAhead* la = lookahead_for_current_device();
+  if (!la) return GPINV_ERR_CUDA;
+  GPINV_TRY(cudaStreamWaitEvent(st, la->evW, 0));
+  return GPINV_OK;
+}
 
 // Solve X L^T = B in place (B is m x n row-major, L n x n lower): forward substitution over
 // columns, i.e. row-wise "L x = b" for every row of B.  Used by the whitened conditional

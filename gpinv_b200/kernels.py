@@ -169,7 +169,10 @@ class Stationary(Kern):
         if type(self)._Kcore is not Stationary._Kcore:
             return Kern.Cholesky_factor(self, X)      # a subclass with its own core: generic path
         Xs, _ = self._slice(X, None)
-        chol, info = ops.chol_core(Xs, self.lengthscales, self._mode, float(settings.numerics.jitter_level))
+        # the reverse pass needs L^-1: have it built behind the factorisation, on the side stream
+        need_inv = torch.is_grad_enabled() and self.lengthscales.requires_grad
+        chol, info, _ = ops.chol_core(Xs, self.lengthscales, self._mode, float(settings.numerics.jitter_level),
+                                      bool(need_inv))
         return CholeskyFactor([chol], torch.sqrt(self.variance), [0] * self.output_dim, [info])
 
     def __str__(self):

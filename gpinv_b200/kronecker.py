@@ -50,8 +50,8 @@ class RBF2D(kernels.RBF):
 
     def Cholesky_factor(self, X):
         j = settings.numerics.jitter_level
-        c1, i1 = ops.chol_core(self.dim1.contiguous(), self.lengthscales, self._mode, float(j))
-        c2, i2 = ops.chol_core(self.dim2.contiguous(), self.lengthscales, self._mode, float(j))
+        c1, i1, _ = ops.chol_core(self.dim1.contiguous(), self.lengthscales, self._mode, float(j), False)
+        c2, i2, _ = ops.chol_core(self.dim2.contiguous(), self.lengthscales, self._mode, float(j), False)
         return kernels.CholeskyFactor([(c1, c2)], torch.sqrt(self.variance), [0] * self.output_dim,
                                       [i1, i2], kron=True)
 

@@ -186,10 +186,19 @@ potrf.register_autograd(_potrf_backward, setup_context=_potrf_setup)
 # --------------------------------------------------------------------------------------
 # T1-T4 fused: chol(core(X,X) + jitter I) with the lower-triangle-only build and reverse
 # --------------------------------------------------------------------------------------
+# Explicit inverses built on the library's side stream (see chol_core): the last few are kept alive here
+# so that their memory cannot be handed out again while the side stream may still be writing it (a forward
+# pass whose result is dropped without a reverse pass never joins the side stream); an entry is dropped
+# only after a host-side wait for the side stream.
+_W_KEEP = []
+
+
 @torch.library.custom_op("gpinv::chol_core", mutates_args=(), device_types="cuda")
-def chol_core(X: Tensor, ls: Tensor, mode: int, jitter: float) -> Tuple[Tensor, Tensor]:
-    """(L, info) = Cholesky factor of core(X,X) + jitter*I (GPinv/kernels.py:56-59) in one call:
-    only the lower triangle of the core is evaluated and it is factored in place."""
+def chol_core(X: Tensor, ls: Tensor, mode: int, jitter: float, with_inverse: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """(L, info, W) with L = Cholesky factor of core(X,X) + jitter*I (GPinv/kernels.py:56-59): only the
+    lower triangle of the core is evaluated and it is factored in place.  ``with_inverse``: W = L^-1 is
+    built on a side stream right behind the factorisation -- the reverse pass needs it, it depends on L
+    only, so it overlaps the sampling / likelihood stages that follow -- else W is empty."""
     X = _chk(X, "X")
     ls = _chk(ls, "ls").reshape(-1)
     ensure_workspace(X.device)
@@ -202,13 +211,29 @@ def chol_core(X: Tensor, ls: Tensor, mode: int, jitter: float) -> Tuple[Tensor, 
     rc = lib.gpinv_chol_core_f64(_p(X), n, D, D, _p(ls), ard, mode, float(jitter), _p(Lm), n, _p(info),
                                  _p(ws), _st())
     _capi.check(rc, "chol_core")
-    return Lm, info
+    if with_inverse and n > 64:
+        # W[0] = L^-1, W[1] = scratch of the inversion: ONE tensor, returned and saved for the reverse pass,
+        # so that neither half can be recycled (by the caching allocator, or by a captured graph's pool)
+        # before the reverse pass has joined the side stream
+        W = torch.empty((2, n, n), dtype=torch.float64, device=X.device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing and len(_W_KEEP) >= 4:
+            _capi.check(lib.gpinv_trtri_side_sync(), "trtri_side_sync")      # idle unless a result was dropped
+            del _W_KEEP[0]
+        _capi.check(lib.gpinv_trtri_side_f64(_p(Lm), n, _p(W), C.c_void_p(W.data_ptr() + 8 * n * n), n, _st()),
+                    "trtri_side")
+        if not capturing:       # (inside a capture the tensor lives until the captured reverse pass)
+            _W_KEEP.append(W)
+    else:
+        W = torch.empty(0, dtype=torch.float64, device=X.device)
+    return Lm, info, W
 
 
 @torch.library.custom_op("gpinv::chol_core_bwd", mutates_args=(), device_types="cuda")
-def chol_core_bwd(X: Tensor, ls: Tensor, mode: int, L: Tensor, Lbar: Tensor) -> Tensor:
-    """dObj/d(lengthscales) from dObj/dL: blocked Cholesky reverse sweep kept as a lower triangle
-    and reduced straight into the lengthscale gradient (no symmetric n x n gradient is formed)."""
+def chol_core_bwd(X: Tensor, ls: Tensor, mode: int, L: Tensor, Lbar: Tensor, W: Tensor) -> Tensor:
+    """dObj/d(lengthscales) from dObj/dL: Cholesky reverse (inverse formula, W = L^-1 from the forward
+    pass when available) kept as a lower triangle and reduced straight into the lengthscale gradient
+    (no symmetric n x n gradient is formed)."""
     X = _chk(X, "X")
     ls = _chk(ls, "ls").reshape(-1)
     L = _chk(L, "L")
@@ -219,23 +244,23 @@ def chol_core_bwd(X: Tensor, ls: Tensor, mode: int, L: Tensor, Lbar: Tensor) -> 
     out = torch.empty_like(ls)
     lib = _capi.lib()
     ws = _ws(lib.gpinv_chol_core_bwd_ws_bytes(n, D), X)
-    rc = lib.gpinv_chol_core_bwd_f64(_p(X), n, D, D, _p(ls), ard, mode, _p(L), n, _p(Lbar), n, _p(out),
-                                     _p(ws), _st())
+    rc = lib.gpinv_chol_core_bwd2_f64(_p(X), n, D, D, _p(ls), ard, mode, _p(L), n, _p(Lbar), n,
+                                      _p(W) if W.numel() else None, _p(out), _p(ws), _st())
     _capi.check(rc, "chol_core_bwd")
     return out
 
 
 def _chol_core_setup(ctx, inputs, output):
-    X, ls, mode, jitter = inputs
-    ctx.save_for_backward(X, ls, output[0])
+    X, ls, mode, jitter, with_inverse = inputs
+    ctx.save_for_backward(X, ls, output[0], output[2])
     ctx.mode = mode
     ctx.ls_shape = ls.shape
 
 
-def _chol_core_backward(ctx, Lbar, _info_bar):
-    X, ls, L = ctx.saved_tensors
-    g = chol_core_bwd(X, ls, ctx.mode, L, Lbar.contiguous())
-    return None, g.reshape(ctx.ls_shape), None, None
+def _chol_core_backward(ctx, Lbar, _info_bar, _w_bar):
+    X, ls, L, W = ctx.saved_tensors
+    g = chol_core_bwd(X, ls, ctx.mode, L, Lbar.contiguous(), W)
+    return None, g.reshape(ctx.ls_shape), None, None, None
 
 
 chol_core.register_autograd(_chol_core_backward, setup_context=_chol_core_setup)

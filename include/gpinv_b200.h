@@ -91,6 +91,18 @@ size_t gpinv_chol_core_bwd_ws_bytes(int n, int D);
 int gpinv_chol_core_bwd_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
                             int mode, const double* L, int ldl, const double* Lbar, int ldlb,
                             double* ls_bar, void* ws, void* stream);
+/* Same reverse with the explicit inverse W = L^-1 [n,n] supplied (built ahead of time by
+ * gpinv_trtri_side_f64 on the library's side stream, overlapping the sampling / likelihood stages:
+ * the inverse depends on L only).  The call first makes `stream` wait for that side-stream work. */
+int gpinv_chol_core_bwd2_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
+                             int mode, const double* L, int ldl, const double* Lbar, int ldlb,
+                             const double* Winv, double* ls_bar, void* ws, void* stream);
+/* Winv <- L^-1 on the side stream once the work already enqueued on `stream` is done; `scratch` [n,n].
+ * gpinv_trtri_side_join makes `stream` wait for the most recent such inversion. */
+int gpinv_trtri_side_f64(const double* L, int ldl, double* Winv, double* scratch, int n, void* stream);
+int gpinv_trtri_side_join(void* stream);
+/* host-side wait for the side stream (before an inverse buffer is recycled outside a reverse pass) */
+int gpinv_trtri_side_sync(void);
 /* --- T22: X <- X L^{-T} (row-wise forward substitution; X is m x n).  Replaces
  * tf.batch_matrix_triangular_solve at GPinv/conditionals.py:44 (applied to Kmn^T). */
 int gpinv_trsm_rlt_f64(const double* L, int ldl, double* X, int ldx, int m, int n, void* stream);
