@@ -64,6 +64,11 @@ SIGNATURES = {
     "gpinv_abel_bwd_f64": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),
     "gpinv_spec_fwd_f64": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "gpinv_spec_bwd_f64": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "gpinv_unpack_f64": (_I, [_P, _I, _P, _P, _P, _P]),
+    "gpinv_pack_f64": (_I, [_P, _I, _P, _P, _P, _D, _P, _P]),
+    "gpinv_kl_white_f64": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "gpinv_kl_white_bwd_f64": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "gpinv_adam_step_f64": (_I, [_P, _P, _P, _P, C.c_longlong, _D, _D, _D, _D, _P, _P]),
     "gpinv_sumsq_f64": (_I, [_P, _Z, _P, _P]),
 }
 

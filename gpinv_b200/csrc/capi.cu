@@ -64,6 +64,12 @@ int kron_sample_fwd_f64(const double*, int, const double*, int, const double*, c
 int kron_sample_bwd_f64(const double*, int, const double*, int, const double*, const double*, int, const double*,
                         const double*, const double*, const double*, const double*, int, int, double*, double*,
                         double*, double*, double*, double*, double*, double*, cudaStream_t);
+int unpack_f64(const double*, int, const long long*, const int*, double* const*, cudaStream_t);
+int pack_f64(const double*, int, const long long*, const int*, const double* const*, double, double*, cudaStream_t);
+int kl_white_f64(const double*, const double*, int, int, int, double*, cudaStream_t);
+int kl_white_bwd_f64(const double*, const double*, int, int, int, const double*, double*, double*, cudaStream_t);
+int adam_step_f64(double*, double*, double*, const double*, long long, double, double, double, double, long long*,
+                  cudaStream_t);
 int spec_fwd_f64(const double*, const double*, const double*, const double*, const double*, int, int,
                  int, int, double*, double*, cudaStream_t);
 int spec_bwd_f64(const double*, const double*, const double*, const double*, const double*,
@@ -363,6 +369,34 @@ int gpinv_kron_sample_bwd_f64(const double* L1, int n1, const double* L2, int n2
                               double* mean_bar, void* ws, void* stream) {
   return kron_sample_bwd_f64(L1, n1, L2, n2, sqrt_v, Q, q_diag, E, U, T, Fbar, klbar, S, R, Ubar, qmu_bar, Qbar,
                              L1bar, L2bar, svdot, mean_bar, static_cast<double*>(ws), ST(stream));
+}
+
+int gpinv_unpack_f64(const double* x, int nblocks, const long long* off, const int* transform,
+                     double* const* dst, void* stream) {
+  if (!x || !off || !transform || !dst) return GPINV_ERR_ARG;
+  return unpack_f64(x, nblocks, off, transform, dst, ST(stream));
+}
+
+int gpinv_pack_f64(const double* x, int nblocks, const long long* off, const int* transform,
+                   const double* const* gval, double scale, double* gx, void* stream) {
+  if (!x || !off || !transform || !gval || !gx) return GPINV_ERR_ARG;
+  return pack_f64(x, nblocks, off, transform, gval, scale, gx, ST(stream));
+}
+
+int gpinv_kl_white_f64(const double* q_mu, const double* q_sqrt, int n, int R, int q_diag, double* kl_out,
+                       void* stream) {
+  return kl_white_f64(q_mu, q_sqrt, n, R, q_diag, kl_out, ST(stream));
+}
+
+int gpinv_kl_white_bwd_f64(const double* q_mu, const double* q_sqrt, int n, int R, int q_diag,
+                           const double* gbar, double* mu_bar, double* q_bar, void* stream) {
+  return kl_white_bwd_f64(q_mu, q_sqrt, n, R, q_diag, gbar, mu_bar, q_bar, ST(stream));
+}
+
+int gpinv_adam_step_f64(double* x, double* m, double* v, const double* g, long long count, double lr,
+                        double beta1, double beta2, double epsilon, long long* step, void* stream) {
+  if (!x || !m || !v || !g || !step) return GPINV_ERR_ARG;
+  return adam_step_f64(x, m, v, g, count, lr, beta1, beta2, epsilon, step, ST(stream));
 }
 
 int gpinv_sumsq_f64(const double* x, size_t count, double* out, void* stream) {

@@ -15,23 +15,77 @@ namespace gpinv {
 // ------------------------------ small HBM-bound kernels -------------------------------
 
 // dst[r][i][j] = (j <= i) ? src[(i*n + j)*R + r] : 0      (GPinv/stvgp.py:157 band_part)
-__global__ void tril_unpack_kernel(const double* __restrict__ src, double* __restrict__ dst, int n,
-                                   int R) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// One CTA per (row i, chunk of 256 columns): the chunk's 256*R source doubles are contiguous and are
+// read coalesced (through shared memory when R > 1, so that the R destination rows are written
+// coalesced too); columns above the diagonal are not read at all.  R == 1: 16-byte accesses.
+constexpr int TRIL_JC = 256;
+__global__ void __launch_bounds__(256) tril_unpack_kernel(const double* __restrict__ src, double* __restrict__ dst, int n,
+                                                          int R) {
+  extern __shared__ __align__(16) double tsm[];
   const int i = blockIdx.y;
-  const int r = blockIdx.z;
-  if (j >= n) return;
-  dst[((size_t)r * n + i) * n + j] = (j <= i) ? src[((size_t)i * n + j) * R + r] : 0.0;
+  const int j0 = blockIdx.x * TRIL_JC;
+  const int jn = min(TRIL_JC, n - j0);          // columns of this chunk
+  const int jv = max(0, min(jn, i + 1 - j0));   // ... of which at or below the diagonal
+  if (R == 1) {
+    const double* s = src + (size_t)i * n + j0;
+    double* d = dst + (size_t)i * n + j0;
+    if ((((size_t)i * n + j0) & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+      const int c = 2 * threadIdx.x;
+      if (c + 1 < jn) {
+        double2 v = make_double2(0.0, 0.0);
+        if (c + 1 < jv) v = *reinterpret_cast<const double2*>(s + c);
+        else if (c < jv) v.x = s[c];
+        *reinterpret_cast<double2*>(d + c) = v;
+      } else if (c < jn) {
+        d[c] = (c < jv) ? s[c] : 0.0;
+      }
+    } else {
+      for (int c = threadIdx.x; c < jn; c += blockDim.x) d[c] = (c < jv) ? s[c] : 0.0;
+    }
+    return;
+  }
+  const double* s = src + ((size_t)i * n + j0) * R;
+  for (int k = threadIdx.x; k < jv * R; k += blockDim.x) tsm[k] = s[k];
+  __syncthreads();
+  for (int r = 0; r < R; ++r) {
+    double* d = dst + ((size_t)r * n + i) * n + j0;
+    for (int c = threadIdx.x; c < jn; c += blockDim.x) d[c] = (c < jv) ? tsm[c * R + r] : 0.0;
+  }
 }
 
 // dst[(i*n + j)*R + r] = (j <= i) ? src[r][i][j] : 0     (reverse of tril_unpack)
-__global__ void tril_pack_kernel(const double* __restrict__ src, double* __restrict__ dst, int n,
-                                 int R) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) tril_pack_kernel(const double* __restrict__ src, double* __restrict__ dst, int n,
+                                                        int R) {
+  extern __shared__ __align__(16) double tsm[];
   const int i = blockIdx.y;
-  const int r = blockIdx.z;
-  if (j >= n) return;
-  dst[((size_t)i * n + j) * R + r] = (j <= i) ? src[((size_t)r * n + i) * n + j] : 0.0;
+  const int j0 = blockIdx.x * TRIL_JC;
+  const int jn = min(TRIL_JC, n - j0);
+  const int jv = max(0, min(jn, i + 1 - j0));
+  if (R == 1) {
+    const double* s = src + (size_t)i * n + j0;
+    double* d = dst + (size_t)i * n + j0;
+    if ((((size_t)i * n + j0) & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+      const int c = 2 * threadIdx.x;
+      if (c + 1 < jn) {
+        double2 v = make_double2(0.0, 0.0);
+        if (c + 1 < jv) v = *reinterpret_cast<const double2*>(s + c);
+        else if (c < jv) v.x = s[c];
+        *reinterpret_cast<double2*>(d + c) = v;
+      } else if (c < jn) {
+        d[c] = (c < jv) ? s[c] : 0.0;
+      }
+    } else {
+      for (int c = threadIdx.x; c < jn; c += blockDim.x) d[c] = (c < jv) ? s[c] : 0.0;
+    }
+    return;
+  }
+  for (int r = 0; r < R; ++r) {
+    const double* s = src + ((size_t)r * n + i) * n + j0;
+    for (int c = threadIdx.x; c < jv; c += blockDim.x) tsm[c * R + r] = s[c];
+  }
+  __syncthreads();
+  double* d = dst + ((size_t)i * n + j0) * R;
+  for (int k = threadIdx.x; k < jn * R; k += blockDim.x) d[k] = (k < jv * R) ? tsm[k] : 0.0;
 }
 
 // *out += sum x^2 ; 128-bit loads when aligned
@@ -204,15 +258,17 @@ static inline int ew_grid(size_t total) {
 // ------------------------------------ host drivers ------------------------------------
 
 int tril_unpack_f64(const double* src, double* dst, int n, int R, cudaStream_t st) {
-  dim3 grid(cdiv(n, 256), n, R);
-  tril_unpack_kernel<<<grid, 256, 0, st>>>(src, dst, n, R);
+  if (R > 16) return GPINV_ERR_ARG;
+  dim3 grid(cdiv(n, TRIL_JC), n);
+  tril_unpack_kernel<<<grid, R == 1 ? 128 : 256, R == 1 ? 0 : TRIL_JC * R * sizeof(double), st>>>(src, dst, n, R);
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
 }
 
 int tril_pack_f64(const double* src, double* dst, int n, int R, cudaStream_t st) {
-  dim3 grid(cdiv(n, 256), n, R);
-  tril_pack_kernel<<<grid, 256, 0, st>>>(src, dst, n, R);
+  if (R > 16) return GPINV_ERR_ARG;
+  dim3 grid(cdiv(n, TRIL_JC), n);
+  tril_pack_kernel<<<grid, R == 1 ? 128 : 256, R == 1 ? 0 : TRIL_JC * R * sizeof(double), st>>>(src, dst, n, R);
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
 }

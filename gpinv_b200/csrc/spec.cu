@@ -8,14 +8,18 @@
 
 namespace gpinv {
 
-#define SPEC_MAX_N 2048
+constexpr int SPEC_MAX_N = 9000;     // 3 n doubles of shared memory (<= 216 KB with the opt-in limit)
 constexpr double INV_SQRT_2PI = 0.3989422804014326779399460599343819;
 
-// grid (ceil(k*m/256), S); thread = one (wavelength, chord) pair, wavelength fastest so a warp
-// shares the chord row of A / cosT (broadcast loads).
+// A and cosTheta are passed TRANSPOSED ([n, m]: chord index contiguous): with one thread per
+// (chord, wavelength) pair and the chord index fastest, a warp reads 32 consecutive chords of a radial
+// shell in one 256-byte transaction, and P / Y ([.., k, m], chord fastest) are read and written
+// coalesced as well.  (The first version read the [m, n] originals with a stride of n doubles.)
+
+// grid (ceil(k*m/256), S); thread = one (wavelength kk, chord mm) pair, chord fastest.
 __global__ void __launch_bounds__(256) spec_fwd_kernel(const double* __restrict__ F,
-                                                       const double* __restrict__ A,
-                                                       const double* __restrict__ cosT,
+                                                       const double* __restrict__ At,
+                                                       const double* __restrict__ cosTt,
                                                        const double* __restrict__ lam,
                                                        const double* __restrict__ Y, int n, int m,
                                                        int k, int S, double* __restrict__ P,
@@ -38,14 +42,14 @@ __global__ void __launch_bounds__(256) spec_fwd_kernel(const double* __restrict_
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double d2 = 0.0;
   if (p < k * m) {
-    const int mm = p / k, kk = p % k;
+    const int kk = p / m, mm = p % m;
     const double l = lam[kk];
-    const double* a_row = A + (size_t)mm * n;
-    const double* c_row = cosT + (size_t)mm * n;
     double acc = 0.0;
+#pragma unroll 4
     for (int j = 0; j < n; ++j) {
-      const double z = (l - vel[j] * c_row[j]) * invs[j];
-      acc += a_row[j] * amp[j] * exp(-0.5 * z * z);
+      const double a = At[(size_t)j * m + mm];
+      const double z = (l - vel[j] * cosTt[(size_t)j * m + mm]) * invs[j];
+      acc += a * amp[j] * exp(-0.5 * z * z);
     }
     if (P) P[((size_t)s * k + kk) * m + mm] = acc;
     if (Y) {
@@ -62,8 +66,8 @@ __global__ void __launch_bounds__(256) spec_fwd_kernel(const double* __restrict_
 // grid (n, S); one block reduces over all (k,m) pairs for one (sample, radial point):
 //   Fbar_c[s,j] = coef * sum_{k,m} (P - Y) dt/dF_c
 __global__ void __launch_bounds__(256) spec_bwd_kernel(const double* __restrict__ F,
-                                                       const double* __restrict__ A,
-                                                       const double* __restrict__ cosT,
+                                                       const double* __restrict__ At,
+                                                       const double* __restrict__ cosTt,
                                                        const double* __restrict__ lam,
                                                        const double* __restrict__ Y,
                                                        const double* __restrict__ P,
@@ -77,13 +81,15 @@ __global__ void __launch_bounds__(256) spec_bwd_kernel(const double* __restrict_
   const double is = exp(-f1);
   const double amp = exp(f0) * is * INV_SQRT_2PI;
   const double v = F[2 * Sn + (size_t)s * n + j];
+  const double* a_row = At + (size_t)j * m;        // chord index contiguous
+  const double* c_row = cosTt + (size_t)j * m;
   double g0 = 0.0, g1 = 0.0, g2 = 0.0;
   const int total = k * m;
   for (int p = threadIdx.x; p < total; p += blockDim.x) {
-    const int kk = p / m, mm = p % m;   // chord fastest: P and Y reads are coalesced
-    const double a = A[(size_t)mm * n + j];
+    const int kk = p / m, mm = p % m;   // chord fastest: A, cosT, P and Y reads are all coalesced
+    const double a = a_row[mm];
     if (a == 0.0) continue;
-    const double ct = cosT[(size_t)mm * n + j];
+    const double ct = c_row[mm];
     const double z = (lam[kk] - v * ct) * is;
     const double t = a * amp * exp(-0.5 * z * z);
     const double r = P[((size_t)s * k + kk) * m + mm] - Y[(size_t)kk * m + mm];
@@ -101,23 +107,35 @@ __global__ void __launch_bounds__(256) spec_bwd_kernel(const double* __restrict_
   if (threadIdx.x == 0) Fbar[2 * Sn + (size_t)s * n + j] = c * g2;
 }
 
-int spec_fwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
+// At, cosTt: the [m, n] geometry matrices TRANSPOSED to [n, m]
+int spec_fwd_f64(const double* F, const double* At, const double* cosTt, const double* lam,
                  const double* Y, int n, int m, int k, int S, double* P, double* sumsq,
                  cudaStream_t st) {
   if (n <= 0 || n > SPEC_MAX_N || m <= 0 || k <= 0 || S <= 0) return GPINV_ERR_ARG;
+  const int smem = 3 * n * (int)sizeof(double);
+  if (smem > 48 * 1024) {
+    static bool attr[64] = {};
+    int dev = 0;
+    GPINV_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!attr[dev]) {
+      GPINV_TRY(cudaFuncSetAttribute(spec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * SPEC_MAX_N * 8));
+      attr[dev] = true;
+    }
+  }
   if (sumsq) GPINV_TRY(cudaMemsetAsync(sumsq, 0, sizeof(double), st));
   dim3 grid(cdiv(k * m, 256), S);
-  spec_fwd_kernel<<<grid, 256, 3 * n * sizeof(double), st>>>(F, A, cosT, lam, Y, n, m, k, S, P, sumsq);
+  spec_fwd_kernel<<<grid, 256, smem, st>>>(F, At, cosTt, lam, Y, n, m, k, S, P, sumsq);
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
 }
 
-int spec_bwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
+int spec_bwd_f64(const double* F, const double* At, const double* cosTt, const double* lam,
                  const double* Y, const double* P, const double* coef, int n, int m, int k, int S,
                  double* Fbar, cudaStream_t st) {
   if (n <= 0 || m <= 0 || k <= 0 || S <= 0) return GPINV_ERR_ARG;
   dim3 grid(n, S);
-  spec_bwd_kernel<<<grid, 256, 0, st>>>(F, A, cosT, lam, Y, P, coef, n, m, k, S, Fbar);
+  spec_bwd_kernel<<<grid, 256, 0, st>>>(F, At, cosTt, lam, Y, P, coef, n, m, k, S, Fbar);
   GPINV_CHECK_LAUNCH();
   return GPINV_OK;
 }

@@ -113,10 +113,21 @@ class SpecAbelLikelihood(Likelihood):
         self.cosT = DataHolder(cosTheta)
         self.lam = DataHolder(np.asarray(lam, dtype=np.float64).reshape(-1, 1))
         self.variance = Param(np.ones(1), transforms.positive)
+        # kernel layout of the geometry: transposed to [n,m] (chord index contiguous).  Kept as data
+        # holders that follow Amat / cosT (refreshed in place when those get new data of the same shape,
+        # so a captured CUDA graph keeps reading valid memory)
+        self._AmatT = DataHolder(np.ascontiguousarray(np.asarray(Amat, dtype=np.float64).T))
+        self._cosTT = DataHolder(np.ascontiguousarray(np.asarray(cosTheta, dtype=np.float64).T))
+        self.Amat._on_change = lambda arr: self._AmatT.set_data(np.ascontiguousarray(arr.T))
+        self.cosT._on_change = lambda arr: self._cosTT.set_data(np.ascontiguousarray(arr.T))
+
+    def _geometry_T(self):
+        return self._AmatT, self._cosTT
 
     def sample_F(self, F):
         """[S,k,m] transformed samples (fused sm_100a kernel)."""
-        return ops.spec_transform(_internal(F), self.Amat, self.cosT, self.lam.reshape(-1).contiguous())
+        At, cTt = self._geometry_T()
+        return ops.spec_transform(_internal(F), At, cTt, self.lam.reshape(-1).contiguous())
 
     def sample_F_torch(self, F):
         """The notebook's tile-and-reduce formulation in torch ops (kept for user subclasses)."""
@@ -132,8 +143,8 @@ class SpecAbelLikelihood(Likelihood):
         return densities.gaussian(f_samples, Y[None].expand(f_samples.shape[0], -1, -1), self.variance)
 
     def logp_sum(self, F, Y, expF=None):
-        ss, P = ops.spec_resid(_internal(F), self.Amat, self.cosT, self.lam.reshape(-1).contiguous(),
-                               Y.contiguous())
+        At, cTt = self._geometry_T()
+        ss, P = ops.spec_resid(_internal(F), At, cTt, self.lam.reshape(-1).contiguous(), Y.contiguous())
         var = self.variance
         return -0.5 * float(P.numel()) * (LOG2PI + torch.log(var)) - 0.5 * ss / var
 

@@ -127,13 +127,17 @@ class Model(Parameterized):
         graph.replay()
         self._pending_infos = list(infos)
         if self.dist is not None:
-            self.dist.all_reduce(f._base if f._base is not None else torch.cat([f, g]))
+            self.dist.all_reduce(f._base)          # f and g are views of one buffer
         return f, g
 
     def _objective_eager(self, x: torch.Tensor, reduce=True, **kw):
         """One evaluation, launched kernel by kernel.  ``reduce=False`` (graph capture under
         sample sharding) returns this rank's partial [-f, -grad] without the all-reduce."""
         self._prepare()
+        if not (reduce and self.dist is not None and self.dist.world_size > 1):
+            out = self._objective_fused(x, reduce=reduce, **kw)
+            if out is not None:
+                return out
         leaves = self.make_tensors(x)
         self._pending_infos = []
         early = {}
@@ -175,6 +179,39 @@ class Model(Parameterized):
         if reduce and self.dist is not None:
             self.dist.all_reduce(buf)
         return buf[:1], buf[1:]
+
+    def _objective_fused(self, x, reduce=True, **kw):
+        """The evaluation with the free state unpacked by one kernel and the gradient packed (chain
+        rule of the positive transform included) by one kernel, straight into the [gradient, value]
+        buffer: no per-parameter softplus / sigmoid / zero-fill / concatenation passes.  None when
+        a parameter uses a transform the kernels do not know (then the generic path runs)."""
+        leaf = self.make_tensors_fused(x)
+        if leaf is None:
+            return None
+        self._pending_infos = []
+        try:
+            with self.tensor_mode():
+                f = self.build_likelihood(**kw)
+                prior = self.build_prior()
+                if prior is not None:
+                    f = f + (prior if self.dist is None else prior / self.dist.world_size)
+            nf = -f.reshape(())
+            (gx,) = torch.autograd.grad(nf, [leaf], allow_unused=True)
+        finally:
+            self.clear_tensors()
+        n = x.numel()
+        if gx is None:
+            gx = torch.zeros(n, dtype=torch.float64, device=x.device)
+        st = gx.untyped_storage()
+        if gx.is_contiguous() and gx.storage_offset() == 0 and gx.numel() == n and st.nbytes() >= 8 * (n + 1):
+            # pack_grad left one slot behind the gradient: [gradient, value] without a concatenation
+            buf = torch.empty(0, dtype=torch.float64, device=x.device).set_(st, 0, (n + 1,))
+            buf[n:].copy_(nf.detach().reshape(1))
+        else:                                           # a prior contributed through a second path: summed copy
+            buf = torch.cat([gx.reshape(-1), nf.detach().reshape(1)])
+        if reduce and self.dist is not None:
+            self.dist.all_reduce(buf)
+        return buf[n:], buf[:n]
 
     def _check_infos(self):
         infos, self._pending_infos = self._pending_infos, []
@@ -533,7 +570,75 @@ class Model(Parameterized):
             return None
         return result
 
+    def _optimize_adam_device(self, method, callback, maxiter, callback_every=1, callback_device=False, **kw):
+        """Training loop with TensorFlow's Adam update fused on the device (the loop shape of
+        GPinv/model.py:206-240 driving tf.train.AdamOptimizer as in testing/test_stvgp.py:31-35): the
+        state x, both moments and the step counter live in HBM, the draws are refilled in place, and
+        with ``enable_cuda_graph()`` one step = ONE graph replay (evaluation + gradient packing + Adam
+        update; nothing is copied, nothing synchronises).  ``callback`` receives the state every
+        ``callback_every`` steps: a numpy copy (reference behaviour), or the device tensor itself
+        with ``callback_device=True`` (no transfer)."""
+        from . import ops
+        dev = default_device()
+        x = torch.as_tensor(self.get_free_state()).to(dev).contiguous()
+        m, v = torch.zeros_like(x), torch.zeros_like(x)
+        step = torch.zeros(1, dtype=torch.int64, device=dev)
+        hp = (float(method.learning_rate), float(method.kw["betas"][0]), float(method.kw["betas"][1]),
+              float(method.kw["eps"]))
+        dyn = self._graph_inputs({})                 # StVGP: {"eps": draws}; GPMC: {}
+        graph = None
+        if self._use_graph and self.dist is None:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):            # warm-up on copies: lazy initialisation, plans
+                xw = x.clone()
+                for _ in range(2):
+                    self._objective_eager(xw, reduce=False, **dyn)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            import gc
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    f, g = self._objective_eager(x, reduce=False, **dyn)
+                    ops.adam_step(x, m, v, g.contiguous(), step, *hp)
+            finally:
+                if gc_was_on:
+                    gc.enable()
+            self._adam_graph = (graph, x, m, v, step, dyn, f, g)     # keeps the captured buffers alive
+        it = 0
+        f = None
+        try:
+            while it < maxiter:
+                if it > 0 or graph is not None:
+                    self._refill_graph_inputs(dyn)   # fresh draws, in place
+                if graph is not None:
+                    graph.replay()
+                else:
+                    f, g = self._objective_device(x, **dyn)
+                    ops.adam_step(x, m, v, g.contiguous(), step, *hp)
+                it += 1
+                if callback is not None and it % max(1, int(callback_every)) == 0:
+                    callback(x if callback_device else x.detach().cpu().numpy())
+        except KeyboardInterrupt:
+            print("Caught KeyboardInterrupt, setting model with most recent state.")
+        xf = x.detach().cpu().numpy()
+        self._check_infos()
+        self.set_state(xf)
+        fun, jac = self._objective(xf)
+        return OptimizeResult(fun=fun, jac=jac, x=xf, nit=it, success=True, status="Finished iterations.")
+
+    def _refill_graph_inputs(self, dyn):
+        """New values for the evaluation's varying inputs, written in place (StVGP: eps draws)."""
+
     def _optimize_torch(self, method, callback, maxiter, **kw):
+        from . import train
+        if isinstance(method, train.AdamOptimizer):
+            return self._optimize_adam_device(method, callback, maxiter, **kw)
         dev = default_device()
         x = torch.as_tensor(self.get_free_state()).to(dev)
         x.requires_grad_(False)

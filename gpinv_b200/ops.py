@@ -577,10 +577,11 @@ def sumsq(x: Tensor) -> Tensor:
 # --------------------------------------------------------------------------------------
 @torch.library.custom_op("gpinv::spec_transform", mutates_args=(), device_types="cuda")
 def spec_transform(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor) -> Tensor:
-    """P [S,k,m] from F [3,S,n] (notebooks/Spectroscopic_Abel_inversion.ipynb:316-346)."""
+    """P [S,k,m] from F [3,S,n] (notebooks/Spectroscopic_Abel_inversion.ipynb:316-346).
+    A, cosT: the geometry matrices TRANSPOSED to [n,m] (see ``likelihoods.SpecAbelLikelihood``)."""
     F = _chk(F, "F"); A = _chk(A, "A"); cosT = _chk(cosT, "cosT"); lam = _chk(lam, "lam")
     _, S, n = F.shape
-    m, k = A.shape[0], lam.numel()
+    m, k = A.shape[1], lam.numel()
     P = torch.empty((S, k, m), dtype=torch.float64, device=F.device)
     rc = _capi.lib().gpinv_spec_fwd_f64(_p(F), _p(A), _p(cosT), _p(lam), None, n, m, k, S, _p(P), None, _st())
     _capi.check(rc, "spec_fwd")
@@ -589,10 +590,10 @@ def spec_transform(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor) -> Tensor:
 
 @torch.library.custom_op("gpinv::spec_resid", mutates_args=(), device_types="cuda")
 def spec_resid(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, Y: Tensor) -> Tuple[Tensor, Tensor]:
-    """(sum (P - Y)^2 [1], P [S,k,m])."""
+    """(sum (P - Y)^2 [1], P [S,k,m]); A, cosT transposed to [n,m]."""
     F = _chk(F, "F"); A = _chk(A, "A"); cosT = _chk(cosT, "cosT"); lam = _chk(lam, "lam"); Y = _chk(Y, "Y")
     _, S, n = F.shape
-    m, k = A.shape[0], lam.numel()
+    m, k = A.shape[1], lam.numel()
     P = torch.empty((S, k, m), dtype=torch.float64, device=F.device)
     ss = torch.empty(1, dtype=torch.float64, device=F.device)
     rc = _capi.lib().gpinv_spec_fwd_f64(_p(F), _p(A), _p(cosT), _p(lam), _p(Y), n, m, k, S, _p(P), _p(ss), _st())
@@ -604,7 +605,7 @@ def spec_resid(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, Y: Tensor) -> Tu
 def spec_bwd(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, Y: Tensor, P: Tensor, coef: Tensor) -> Tensor:
     F = _chk(F, "F"); P = _chk(P, "P"); coef = _chk(coef, "coef")
     _, S, n = F.shape
-    m, k = A.shape[0], lam.numel()
+    m, k = A.shape[1], lam.numel()
     out = torch.empty_like(F)
     rc = _capi.lib().gpinv_spec_bwd_f64(_p(F), _p(A), _p(cosT), _p(lam), _p(Y), _p(P), _p(coef), n, m, k, S,
                                         _p(out), _st())
@@ -623,3 +624,109 @@ def _spec_backward(ctx, g_ss, g_p_unused):
 
 
 spec_resid.register_autograd(_spec_backward, setup_context=_spec_setup)
+
+
+# --------------------------------------------------------------------------------------
+# T19: packed free state <-> constrained parameter blocks, one kernel each way
+# --------------------------------------------------------------------------------------
+def _pack_args(offsets, transforms, tensors):
+    nb = len(transforms)
+    off = (C.c_longlong * (nb + 1))(*offsets)
+    tr = (C.c_int * nb)(*transforms)
+    ptrs = (C.c_void_p * nb)(*[None if t is None else t.data_ptr() for t in tensors])
+    return nb, off, tr, ptrs
+
+
+@torch.library.custom_op("gpinv::unpack_state", mutates_args=(), device_types="cuda")
+def unpack_state(x: Tensor, offsets: List[int], transforms: List[int]) -> List[Tensor]:
+    """Constrained values of every parameter block of the packed free state ``x`` (GPflow
+    ``set_state`` with transforms.positive = softplus + 1e-6) in ONE kernel.  ``offsets`` has one
+    entry more than ``transforms`` (0 identity, 1 positive); block b is a flat tensor."""
+    x = _chk(x, "x")
+    outs = [torch.empty(offsets[b + 1] - offsets[b], dtype=torch.float64, device=x.device)
+            for b in range(len(transforms))]
+    nb, off, tr, ptrs = _pack_args(offsets, transforms, outs)
+    _capi.check(_capi.lib().gpinv_unpack_f64(_p(x), nb, off, tr, ptrs, _st()), "unpack")
+    return outs
+
+
+@torch.library.custom_op("gpinv::pack_grad", mutates_args=(), device_types="cuda")
+def pack_grad(x: Tensor, offsets: List[int], transforms: List[int], grads: List[Optional[Tensor]]) -> Tensor:
+    """d/dx from the gradients w.r.t. the constrained blocks (chain rule sigmoid(x) for positive
+    blocks, zeros where a block received no gradient), written straight into the packed layout."""
+    x = _chk(x, "x")
+    gs = [None if g is None else _chk(g, "grad").reshape(-1) for g in grads]
+    # one extra slot behind the gradient: Model puts the objective value there, so that [gradient, value]
+    # is one contiguous buffer (one all-reduce / one host copy) without a concatenation pass
+    out = torch.empty(x.numel() + 1, dtype=torch.float64, device=x.device)[:x.numel()]
+    nb, off, tr, ptrs = _pack_args(offsets, transforms, gs)
+    _capi.check(_capi.lib().gpinv_pack_f64(_p(x), nb, off, tr, ptrs, 1.0, _p(out), _st()), "pack")
+    return out
+
+
+def _unpack_setup(ctx, inputs, output):
+    x, offsets, transforms = inputs
+    ctx.save_for_backward(x)
+    ctx.offsets, ctx.transforms = list(offsets), list(transforms)
+
+
+def _unpack_backward(ctx, grads):
+    (x,) = ctx.saved_tensors
+    gs = [None if g is None else g.contiguous() for g in grads]
+    return pack_grad(x, ctx.offsets, ctx.transforms, gs), None, None
+
+
+unpack_state.register_autograd(_unpack_backward, setup_context=_unpack_setup)
+
+
+# --------------------------------------------------------------------------------------
+# analytic whitened KL (GPinv/stvgp.py:187-195)
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("gpinv::kl_white", mutates_args=(), device_types="cuda")
+def kl_white(q_mu: Tensor, q_sqrt: Tensor, q_diag: bool) -> Tensor:
+    """GPflow gauss_kl_white[_diag]: q_mu [n,R]; q_sqrt [n,n,R] (lower triangle read) or [n,R]."""
+    q_mu = _chk(q_mu, "q_mu"); q_sqrt = _chk(q_sqrt, "q_sqrt")
+    n, R = q_mu.shape
+    out = torch.empty(4, dtype=torch.float64, device=q_mu.device)
+    _capi.check(_capi.lib().gpinv_kl_white_f64(_p(q_mu), _p(q_sqrt), n, R, int(q_diag), _p(out), _st()), "kl_white")
+    return out[:1].clone()
+
+
+@torch.library.custom_op("gpinv::kl_white_bwd", mutates_args=(), device_types="cuda")
+def kl_white_bwd(q_mu: Tensor, q_sqrt: Tensor, q_diag: bool, gbar: Tensor) -> List[Tensor]:
+    q_mu = _chk(q_mu, "q_mu"); q_sqrt = _chk(q_sqrt, "q_sqrt"); gbar = _chk(gbar, "gbar")
+    n, R = q_mu.shape
+    mu_bar, q_bar = torch.empty_like(q_mu), torch.empty_like(q_sqrt)
+    _capi.check(_capi.lib().gpinv_kl_white_bwd_f64(_p(q_mu), _p(q_sqrt), n, R, int(q_diag), _p(gbar), _p(mu_bar),
+                                                   _p(q_bar), _st()), "kl_white_bwd")
+    return [mu_bar, q_bar]
+
+
+def _klw_setup(ctx, inputs, output):
+    q_mu, q_sqrt, q_diag = inputs
+    ctx.save_for_backward(q_mu, q_sqrt)
+    ctx.q_diag = q_diag
+
+
+def _klw_backward(ctx, g):
+    q_mu, q_sqrt = ctx.saved_tensors
+    mu_bar, q_bar = kl_white_bwd(q_mu, q_sqrt, ctx.q_diag, g.reshape(1).contiguous())
+    return mu_bar, q_bar, None
+
+
+kl_white.register_autograd(_klw_backward, setup_context=_klw_setup)
+
+
+# --------------------------------------------------------------------------------------
+# optimiser step on the device-resident state
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("gpinv::adam_step", mutates_args=("x", "m", "v", "step"), device_types="cuda")
+def adam_step(x: Tensor, m: Tensor, v: Tensor, g: Tensor, step: Tensor, lr: float, beta1: float, beta2: float,
+              epsilon: float) -> None:
+    """TensorFlow's AdamOptimizer update in place (tf.train.AdamOptimizer at testing/test_stvgp.py:31-35);
+    ``step`` is a device int64 [1] advanced by the call, so the launch can sit in a CUDA graph."""
+    for t, nm in ((x, "x"), (m, "m"), (v, "v"), (g, "g")):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            raise RuntimeError("adam_step: %s must be a contiguous fp64 CUDA tensor" % nm)
+    _capi.check(_capi.lib().gpinv_adam_step_f64(_p(x), _p(m), _p(v), _p(g), x.numel(), float(lr), float(beta1),
+                                                float(beta2), float(epsilon), _p(step), _st()), "adam_step")

@@ -86,6 +86,7 @@ class Param(Parentable):
         self.prior = None
         self._tensor = None
         self._free_leaf = None
+        self._free_slice = None     # (x leaf, begin, end) when the tensor came from the fused unpack
         self._before_use = None     # optional callable run once before the tensor is first read
         self._tril_rows = None      # n if the value is one row-major [n,n] matrix read as tril() only
 
@@ -158,6 +159,7 @@ class DataHolder(Parentable):
         assert on_shape_change in ("raise", "pass", "recompile")
         self.on_shape_change = on_shape_change
         self._tensor = None
+        self._on_change = None      # optional callable(array) run after set_data (derived layouts)
 
     @property
     def value(self):
@@ -181,6 +183,8 @@ class DataHolder(Parentable):
             self._array = array
             self._tensor = None
             _STATE_EPOCH[0] += 1
+        if self._on_change is not None:
+            self._on_change(array)
 
     def tensor(self):
         if self._tensor is None:
@@ -319,10 +323,53 @@ class Parameterized(Parentable):
             raise ValueError("state vector has %d entries, the model has %d free parameters" % (x.numel(), off))
         return leaves
 
+    def fused_layout(self):
+        """(free params, offsets, transform codes) for the one-kernel unpack / pack of the free state, or
+        None when a free Param uses a transform the kernels do not implement (identity and
+        ``transforms.positive`` are built in; anything else takes the per-Param torch path)."""
+        params = [p for p in self.all_params() if not p.fixed]
+        offs, codes = [0], []
+        for p in params:
+            tr = p.transform
+            if isinstance(tr, transforms.Identity):
+                codes.append(0)
+            elif isinstance(tr, transforms.Log1pe) and tr._lower == 1e-6:
+                codes.append(1)
+            else:
+                return None
+            offs.append(offs[-1] + p.size)
+        if not params or len(params) > 32:
+            return None
+        return params, offs, codes
+
+    def make_tensors_fused(self, x: torch.Tensor):
+        """Like ``make_tensors`` with ONE kernel for every block (``gpinv::unpack_state``; its reverse packs
+        the gradient, chain rule included, in one kernel too).  Returns the single leaf (``x`` itself,
+        requiring grad) or None when the layout is not supported."""
+        lay = self.fused_layout()
+        if lay is None:
+            return None
+        from . import ops
+        params, offs, codes = lay
+        if offs[-1] != x.numel():
+            raise ValueError("state vector has %d entries, the model has %d free parameters" % (x.numel(), offs[-1]))
+        for p in self.all_params():
+            if p.fixed:
+                p._tensor = p.fixed_tensor(x.device)
+                p._free_leaf = None
+        leaf = x.detach().requires_grad_(True)
+        vals = ops.unpack_state(leaf, offs, codes)
+        for i, (p, v) in enumerate(zip(params, vals)):
+            p._tensor = v.view(p.shape)
+            p._free_leaf = None
+            p._free_slice = (leaf, offs[i], offs[i + 1])
+        return leaf
+
     def clear_tensors(self):
         for p in self.all_params():
             p._tensor = None
             p._free_leaf = None
+            p._free_slice = None
 
     def build_prior(self):
         """sum of log priors (+ log-Jacobian of the transform) over params that carry one."""
@@ -330,7 +377,11 @@ class Parameterized(Parentable):
         for p in self.all_params():
             if p.prior is None or p.fixed:
                 continue
-            t = p.prior.logp(p._tensor) + p.transform.torch_log_jacobian(p._free_leaf)
+            leaf = p._free_leaf
+            if leaf is None:                      # fused unpack: the free values are a slice of x
+                xl, a, b = p._free_slice
+                leaf = xl[a:b].view(p.shape)
+            t = p.prior.logp(p._tensor) + p.transform.torch_log_jacobian(leaf)
             total = t if total is None else total + t
         return total
 

@@ -91,6 +91,12 @@ class StVGP(GPModel):
         S = self.num_samples if eps is None else eps.shape[1]
         return {"eps": self._eps_full(eps, S).contiguous()}
 
+    def _refill_graph_inputs(self, dyn):
+        if "eps" in dyn:
+            if self._generator is None:
+                self._draw_eps(1)                     # creates / seeds the device generator
+            dyn["eps"].normal_(generator=self._generator)
+
     def build_likelihood(self, eps=None):
         """Variational lower bound with stochastic approximation (GPinv/stvgp.py:96-107)."""
         S_global = self.num_samples if eps is None else eps.shape[1]
@@ -164,13 +170,6 @@ class StVGP(GPModel):
         return F.permute(1, 2, 0), expF
 
     def _analytical_KL(self):
-        """GPinv/stvgp.py:187-195 -> GPflow gauss_kl_white[_diag]."""
-        q_mu, q_sqrt = self.q_mu, self.q_sqrt
-        KL = 0.5 * torch.sum(torch.square(q_mu)) - 0.5 * float(q_mu.numel())
-        if self.q_diag:
-            KL = KL - 0.5 * torch.sum(torch.log(torch.square(q_sqrt))) + 0.5 * torch.sum(torch.square(q_sqrt))
-        else:
-            Q = ops.tril_unpack(q_sqrt)
-            diag = torch.diagonal(Q, dim1=1, dim2=2)
-            KL = KL - 0.5 * torch.sum(torch.log(torch.square(diag))) + 0.5 * torch.sum(torch.square(Q))
-        return KL
+        """GPinv/stvgp.py:187-195 -> GPflow gauss_kl_white[_diag]; one reduction kernel over q_mu and the
+        lower triangle of q_sqrt in the reference's own [n,n,R] layout (and one for its gradient)."""
+        return ops.kl_white(self.q_mu.contiguous(), self.q_sqrt.contiguous(), bool(self.q_diag)).reshape(())

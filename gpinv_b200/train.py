@@ -15,7 +15,9 @@ class _TorchOptimizer(object):
 
 
 class AdamOptimizer(_TorchOptimizer):
-    """tf.train.AdamOptimizer(learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8)."""
+    """tf.train.AdamOptimizer(learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8).  ``Model.optimize``
+    runs it as TensorFlow's update fused on the device (``gpinv::adam_step``,
+    ``Model._optimize_adam_device``); ``make`` (a torch.optim.Adam) is kept for user loops."""
     _cls = torch.optim.Adam
 
     def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):

@@ -181,15 +181,46 @@ int gpinv_abel_bwd_f64(const double* Rs, const double* A, int lda, const double*
                        const double* coef, int n, int M, int S, double* Fbar, void* stream);
 
 /* --- T16: spectroscopic Abel transform (notebooks/Spectroscopic_Abel_inversion.ipynb:316-356).
- * F [3,S,n] = (log a, log sigma, v); A, cosT [m,n]; lam [k]; Y [k,m] (may be NULL with sumsq).
+ * F [3,S,n] = (log a, log sigma, v); At, cosTt: the notebook's [m,n] geometry matrices TRANSPOSED to
+ * [n,m] (chord index contiguous, so that every access of both kernels is coalesced); lam [k];
+ * Y [k,m] (may be NULL with sumsq); n <= 9000.
  * fwd: P [S,k,m] (may be NULL), *sumsq = sum (P - Y)^2 (may be NULL);
  * bwd: Fbar [3,S,n] = coef * sum_{k,m} (P - Y) dP/dF, coef a device scalar. */
-int gpinv_spec_fwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
+int gpinv_spec_fwd_f64(const double* F, const double* At, const double* cosTt, const double* lam,
                        const double* Y, int n, int m, int k, int S, double* P, double* sumsq,
                        void* stream);
-int gpinv_spec_bwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
+int gpinv_spec_bwd_f64(const double* F, const double* At, const double* cosTt, const double* lam,
                        const double* Y, const double* P, const double* coef, int n, int m, int k,
                        int S, double* Fbar, void* stream);
+
+/* --- T19 and its reverse: the optimiser's packed free state x (GPflow sorted_params order; the x of
+ * GPinv/model.py:64-75) <-> constrained parameter blocks.  Block b covers x[off[b], off[b+1]);
+ * transform[b] = 0 (identity) or 1 (GPflow transforms.positive: y = log(1 + exp(x)) + 1e-6, used at
+ * GPinv/stvgp.py:69, GPinv/likelihoods.py:68 and by the Stationary kernels).  off / transform / dst / gval
+ * are HOST arrays (copied into the launch).  gpinv_unpack_f64 writes the constrained values to dst[b];
+ * gpinv_pack_f64 writes gx[off[b] + k] = scale * gval[b][k] * dy/dx (gval[b] == NULL: zeros), i.e. the
+ * packed gradient that GPflow's _objective closure returns (scale = -1 for "-gradient"). */
+int gpinv_unpack_f64(const double* x, int nblocks, const long long* off, const int* transform,
+                     double* const* dst, void* stream);
+int gpinv_pack_f64(const double* x, int nblocks, const long long* off, const int* transform,
+                   const double* const* gval, double scale, double* gx, void* stream);
+
+/* --- StVGP._analytical_KL (GPinv/stvgp.py:187-195 -> GPflow kullback_leiblers.gauss_kl_white[_diag]):
+ * KL = 1/2 sum m^2 - 1/2 nR - 1/2 sum log Q_ii^2 + 1/2 sum tril(Q)^2 with q_mu [n,R] and q_sqrt in the
+ * reference's layout [n,n,R] (q_diag = 0) or [n,R] (q_diag = 1).  kl_out device [4] = {KL, partial sums}.
+ * Reverse: mu_bar = gbar m, q_bar = gbar (tril(Q) - diag(1/Q_ii)) in the same layouts. */
+int gpinv_kl_white_f64(const double* q_mu, const double* q_sqrt, int n, int R, int q_diag, double* kl_out,
+                       void* stream);
+int gpinv_kl_white_bwd_f64(const double* q_mu, const double* q_sqrt, int n, int R, int q_diag,
+                           const double* gbar, double* mu_bar, double* q_bar, void* stream);
+
+/* --- optimiser step of the training loop (GPinv/model.py:206-240 drives a tf.train optimiser;
+ * testing/test_stvgp.py:31-35: tf.train.AdamOptimizer).  TensorFlow's Adam update in place on the
+ * device-resident state: t = step + 1; lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t);
+ * m = beta1 m + (1 - beta1) g; v = beta2 v + (1 - beta2) g^2; x -= lr_t m / (sqrt(v) + epsilon); step += 1.
+ * `step` is a device int64 so that the launch can be replayed inside a CUDA graph. */
+int gpinv_adam_step_f64(double* x, double* m, double* v, const double* g, long long count, double lr,
+                        double beta1, double beta2, double epsilon, long long* step, void* stream);
 
 /* --- reductions used by T8/T11/T17 */
 int gpinv_sumsq_f64(const double* x, size_t count, double* out, void* stream);

@@ -217,12 +217,12 @@ def check_liks():
         ref = ((Pref - torch.tensor(y)[None]) ** 2).sum()
         (gref,) = torch.autograd.grad(ref, Ft)
         Fd = t(F).requires_grad_(True)
-        ss, P = ops.spec_resid(Fd, t(A), t(cosT), t(lam), t(y))
+        ss, P = ops.spec_resid(Fd, t(A.T.copy()), t(cosT.T.copy()), t(lam), t(y))
         (gout,) = torch.autograd.grad(ss.sum(), Fd)
         report("spec_resid P n=%d m=%d k=%d S=%d" % (n, m, k, S), rel(P, Pref), 1e-13)
         report("spec_resid sumsq", rel(ss, ref.reshape(1)), 1e-13)
         report("spec_resid bwd", rel(gout, gref), 1e-12)
-        report("spec_transform", rel(ops.spec_transform(t(F), t(A), t(cosT), t(lam)), Pref), 1e-13)
+        report("spec_transform", rel(ops.spec_transform(t(F), t(A.T.copy()), t(cosT.T.copy()), t(lam)), Pref), 1e-13)
     x = rng.randn(100001)
     report("sumsq", rel(ops.sumsq(t(x)), torch.tensor([np.sum(x * x)])), 1e-13)
 
@@ -274,10 +274,64 @@ def check_kron():
             report(tag + " d/d" + nm, rel(a, b), 1e-11)
 
 
+def check_pack():
+    """unpack_state / pack_grad (softplus + 1e-6 and its chain rule), the analytic whitened KL and the
+    TensorFlow Adam update against torch / numpy references."""
+    rng = np.random.RandomState(7)
+    sizes = [1, 3, 1, 130, 130 * 130, 7]
+    codes = [1, 1, 1, 0, 0, 1]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    x = rng.randn(offs[-1]) * 2.0
+    x[0] = 40.0
+    x[1] = -40.0
+    xt = torch.tensor(x, requires_grad=True)
+    ref_vals = [(torch.nn.functional.softplus(xt[a:b], threshold=1e9) + 1e-6) if c else xt[a:b]
+                for a, b, c in zip(offs[:-1], offs[1:], codes)]
+    Ws = [torch.tensor(rng.randn(sz)) for sz in sizes]
+    ref_obj = sum((v * w).sum() for i, (v, w) in enumerate(zip(ref_vals, Ws)) if i != 2)     # block 2 unused
+    (gref,) = torch.autograd.grad(ref_obj, xt)
+    xd = t(x).requires_grad_(True)
+    vals = ops.unpack_state(xd, offs, codes)
+    for i, (v, r) in enumerate(zip(vals, ref_vals)):
+        report("unpack_state block %d" % i, rel(v, r), 1e-15)
+    obj = sum((v * w.to(dev)).sum() for i, (v, w) in enumerate(zip(vals, Ws)) if i != 2)
+    (gout,) = torch.autograd.grad(obj, xd)
+    report("pack_grad (chain rule, unused block -> 0)", rel(gout, gref), 1e-15)
+    for (n, R, q_diag) in [(5, 1, False), (40, 3, False), (130, 2, True), (257, 1, False)]:
+        q_mu = rng.randn(n, R)
+        q_sqrt = np.exp(0.3 * rng.randn(n, R)) if q_diag else 0.5 * np.eye(n)[:, :, None] + 0.1 * rng.randn(n, n, R)
+        qm, qs = torch.tensor(q_mu, requires_grad=True), torch.tensor(q_sqrt, requires_grad=True)
+        ref = O.gauss_kl_white_diag(qm, qs) if q_diag else O.gauss_kl_white(qm, qs)
+        gm, gq = torch.autograd.grad(3.0 * ref, [qm, qs])
+        qmd, qsd = t(q_mu).requires_grad_(True), t(q_sqrt).requires_grad_(True)
+        out = ops.kl_white(qmd, qsd, q_diag)
+        gmd, gqd = torch.autograd.grad(3.0 * out.sum(), [qmd, qsd])
+        report("kl_white n=%d R=%d diag=%d" % (n, R, q_diag), rel(out, ref.reshape(1)), 1e-13)
+        report("kl_white d/dq_mu", rel(gmd, gm), 1e-14)
+        report("kl_white d/dq_sqrt (zero above the diagonal)", rel(gqd, gq), 1e-13)
+    # Adam (TensorFlow's formula), 7 steps, odd length
+    n = 1001
+    x0, lr, b1, b2, eps = rng.randn(n), 0.01, 0.9, 0.999, 1e-8
+    gs = [rng.randn(n) for _ in range(7)]
+    xr, mr, vr = x0.copy(), np.zeros(n), np.zeros(n)
+    for k, g in enumerate(gs):
+        tt = k + 1
+        lr_t = lr * np.sqrt(1 - b2 ** tt) / (1 - b1 ** tt)
+        mr = b1 * mr + (1 - b1) * g
+        vr = b2 * vr + (1 - b2) * g * g
+        xr = xr - lr_t * mr / (np.sqrt(vr) + eps)
+    xd, md, vd = t(x0), torch.zeros(n, dtype=torch.float64, device=dev), torch.zeros(n, dtype=torch.float64, device=dev)
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    for g in gs:
+        ops.adam_step(xd, md, vd, t(g), step, lr, b1, b2, eps)
+    report("adam_step x after 7 steps", rel(xd, torch.tensor(xr)), 1e-14)
+    report("adam_step step counter", abs(int(step.item()) - 7), 0.5)
+
+
 if __name__ == "__main__":
     t0 = time.time()
     names = sys.argv[1:] or ["check_gemm", "check_kcore", "check_potrf", "check_trsm", "check_sample", "check_kron",
-                             "check_liks"]
+                             "check_pack", "check_liks"]
     for fn in [globals()[nm] for nm in names]:
         try:
             fn()

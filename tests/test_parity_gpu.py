@@ -640,6 +640,50 @@ def test_dist_attach_refuses_models_without_samples():
         gdist.attach(mc, gdist.DistContext(rank=0, world_size=2))
 
 
+def test_fused_device_adam_matches_a_host_loop():
+    """Model.optimize(train.AdamOptimizer) -- evaluation + gradient packing + TensorFlow's Adam update
+    on the device, eager and as ONE replayed CUDA graph per step -- against the same update applied
+    on the host to gradients from ``_objective`` (loop shape: GPinv/model.py:206-240; optimiser:
+    tf.train.AdamOptimizer, testing/test_stvgp.py:31-35)."""
+    gpmc, kernels, kronecker, likelihoods, mean_functions, stvgp = _gp()
+    from gpinv_b200 import train
+    r, z, A, y = abel_data(30, 40)
+
+    def fresh():
+        mc = gpmc.GPMC(r[:, None], y[:, None], kernels.RBF_csym(1, 1), likelihoods.AbelLikelihood(A), mean_functions.Constant(1))
+        mc.set_state(perturbed_state(mc, 0.3))
+        return mc
+
+    steps, lr, b1, b2, eps = 12, 0.01, 0.9, 0.999, 1e-8
+    mh = fresh()
+    x = mh.get_free_state()
+    mm, vv = np.zeros_like(x), np.zeros_like(x)
+    for k in range(steps):
+        f, g = mh._objective(x)
+        tt = k + 1
+        lr_t = lr * np.sqrt(1 - b2 ** tt) / (1 - b1 ** tt)
+        mm = b1 * mm + (1 - b1) * g
+        vv = b2 * vv + (1 - b2) * g * g
+        x = x - lr_t * mm / (np.sqrt(vv) + eps)
+    for graph in (False, True):
+        md = fresh()
+        md.enable_cuda_graph(graph)
+        seen = []
+        res = md.optimize(train.AdamOptimizer(learning_rate=lr), maxiter=steps, callback=lambda xx: seen.append(xx.copy()),
+                          callback_every=4)
+        assert res.nit == steps and len(seen) == 3
+        assert rel_err(res.x, x) <= 1e-9, (graph, rel_err(res.x, x))
+        assert rel_err(md.get_free_state(), x) <= 1e-9
+    # StVGP: fresh draws every step, refilled in place; the loop must make progress on the ELBO
+    ms = make_abel_stvgp(30, 40, 20, seed=3)
+    ms.enable_cuda_graph()
+    eps0 = np.random.RandomState(0).randn(1, 20, 30)
+    f0, _ = ms._objective(ms.get_free_state(), eps=eps0)
+    ms.optimize(train.AdamOptimizer(learning_rate=0.01), maxiter=150)
+    f1, _ = ms._objective(ms.get_free_state(), eps=eps0)
+    assert f1 < f0 - 1.0, (f0, f1)
+
+
 def test_cholesky_failure_raises():
     gpmc, kernels, kronecker, likelihoods, mean_functions, stvgp = _gp()
     X = np.zeros((8, 1))          # identical points, and a negative jitter would be needed to break it:
