@@ -35,6 +35,11 @@ int trtri_side_join_f64(cudaStream_t);
 int trtri_side_sync_f64();
 int potrf_ex_f64(double*, int, int, int*, int, cudaStream_t);
 int tril_copy_f64(const double*, int, double*, int, int, cudaStream_t);
+int lbar_pack_f64(const double*, int, int, int, int, double*, cudaStream_t);
+int tri_compact_f64(const double*, int, int, double*, cudaStream_t);
+int tri_expand_f64(const double*, double*, int, int, cudaStream_t);
+int potrf_bwd_shard_f64(const double*, int, const double*, int, int, int, const int*, int, const double*, double*,
+                        double*, double*, cudaStream_t);
 int kbuild_ex_f64(const double*, const double*, int, int, int, int, int, const double*, int, int, double,
                   double*, int, double*, int, cudaStream_t);
 int kbuild_bwd_ex_f64(const double*, const double*, int, int, int, int, int, const double*, int, int,
@@ -397,6 +402,35 @@ int gpinv_adam_step_f64(double* x, double* m, double* v, const double* g, long l
                         double beta1, double beta2, double epsilon, long long* step, void* stream) {
   if (!x || !m || !v || !g || !step) return GPINV_ERR_ARG;
   return adam_step_f64(x, m, v, g, count, lr, beta1, beta2, epsilon, step, ST(stream));
+}
+
+int gpinv_lbar_pack_f64(const double* Lbar, int ldlb, int n, int w, int G, double* out, void* stream) {
+  if (!Lbar || !out) return GPINV_ERR_ARG;
+  return lbar_pack_f64(Lbar, ldlb, n, w, G, out, ST(stream));
+}
+
+int gpinv_tri_compact_f64(const double* src, int ld, int n, double* dst, void* stream) {
+  if (!src || !dst) return GPINV_ERR_ARG;
+  return tri_compact_f64(src, ld, n, dst, ST(stream));
+}
+
+int gpinv_tri_expand_f64(const double* src, double* dst, int ld, int n, void* stream) {
+  if (!src || !dst) return GPINV_ERR_ARG;
+  return tri_expand_f64(src, dst, ld, n, ST(stream));
+}
+
+int gpinv_chol_core_bwd_shard_f64(const double* X, int n, int D, int ldx, const double* ls, int ard, int mode,
+                                  const double* L, int ldl, const double* Winv, const double* Dsh, int w,
+                                  const int* c0s, int nblk, double* ls_bar, void* ws, void* stream) {
+  if (n <= 0 || D <= 0 || ldl < n || !Winv || !Dsh || !c0s || nblk <= 0 || w <= 0 || 2 * w > n) return GPINV_ERR_ARG;
+  double* Gacc = static_cast<double*>(ws);            // n x n partial of W^T Phi W
+  double* P = Gacc + (size_t)n * n;                   // n x w
+  double* A = P + (size_t)n * w;                      // n x w
+  double* kws = A + (size_t)n * w;                    // (fits: 2 n w <= n^2 < the sweep's share of the workspace)
+  // (the caller has ordered `stream` after the side-stream inversion: gpinv_trtri_side_join)
+  int rc = potrf_bwd_shard_f64(L, ldl, Winv, n, n, w, c0s, nblk, Dsh, Gacc, P, A, ST(stream));
+  if (rc) return rc;
+  return kbuild_bwd_ex_f64(X, nullptr, n, n, D, ldx, ldx, ls, ard, mode, Gacc, n, ls_bar, kws, 0, ST(stream));
 }
 
 int gpinv_sumsq_f64(const double* x, size_t count, double* out, void* stream) {

@@ -1184,4 +1184,98 @@ int trsm_rlt_f64(const double* L, int ldl, double* X, int ldx, int m, int n, cud
   return GPINV_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Column-block sharded reverse (sample sharding over G GPUs).
+//
+// The reverse of the factorisation is linear in Lbar and only its contraction with dK/d(theta) is
+// needed.  With  G_K = W^T Phi(L^T Lbar) W,  W = L^-1,  column block J of Phi needs column block J of
+// Lbar only, and  G_K = sum_J  (W^T Phi[:,J]) W[J,:].  So the ranks reduce-scatter Lbar by column
+// blocks (instead of each reversing its own partial Lbar over the whole matrix), every rank runs the
+// three products of its blocks -- all with one dimension equal to the block width -- contracts its
+// partial G_K with dK/d(theta), and the scalars are summed with the rest of the gradient.
+// Blocks are dealt in pairs (b, 2G-1-b) of width w = n / 2G, which evens out the triangular work.
+// ---------------------------------------------------------------------------------------
+
+// out: G chunks of (n + w) w doubles; chunk r = [tril-masked Lbar[r w :, block r] ; Lbar[(2G-1-r) w :, block 2G-1-r]]
+__global__ void __launch_bounds__(256) lbar_pack_kernel(const double* __restrict__ Lbar, int ldlb, int n, int w,
+                                                        int G, double* __restrict__ out) {
+  const int i = blockIdx.x;
+  const int ncols = min(n, (i / w + 1) * w);
+  const size_t chunk = (size_t)(n + w) * w;
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+    const int b = c / w, j = c - b * w;
+    const int r = (b < G) ? b : 2 * G - 1 - b;
+    const size_t off = (size_t)r * chunk + ((b < G) ? 0 : (size_t)(n - r * w) * w) + (size_t)(i - b * w) * w + j;
+    out[off] = (c <= i) ? Lbar[(size_t)i * ldlb + c] : 0.0;
+  }
+}
+
+int lbar_pack_f64(const double* Lbar, int ldlb, int n, int w, int G, double* out, cudaStream_t st) {
+  if (n <= 0 || w <= 0 || G <= 0 || 2 * G * w != n || ldlb < n) return GPINV_ERR_ARG;
+  lbar_pack_kernel<<<n, 256, 0, st>>>(Lbar, ldlb, n, w, G, out);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
+// lower triangle (diagonal included) of a row-major matrix <-> packed rows [i (i + 1) / 2 + c]
+__global__ void __launch_bounds__(256) tri_compact_kernel(const double* __restrict__ src, int ld, int n,
+                                                          double* __restrict__ dst) {
+  const int i = blockIdx.x;
+  const size_t o = (size_t)i * (i + 1) / 2;
+  for (int c = threadIdx.x; c <= i; c += blockDim.x) dst[o + c] = src[(size_t)i * ld + c];
+}
+__global__ void __launch_bounds__(256) tri_expand_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                                         int ld, int n) {
+  const int i = blockIdx.x;
+  const size_t o = (size_t)i * (i + 1) / 2;
+  for (int c = threadIdx.x; c <= i; c += blockDim.x) dst[(size_t)i * ld + c] = src[o + c];
+}
+int tri_compact_f64(const double* src, int ld, int n, double* dst, cudaStream_t st) {
+  if (n <= 0 || ld < n) return GPINV_ERR_ARG;
+  tri_compact_kernel<<<n, 256, 0, st>>>(src, ld, n, dst);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+int tri_expand_f64(const double* src, double* dst, int ld, int n, cudaStream_t st) {
+  if (n <= 0 || ld < n) return GPINV_ERR_ARG;
+  tri_expand_kernel<<<n, 256, 0, st>>>(src, dst, ld, n);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
+// Gacc (n x n, ld n) <- sum over this rank's blocks of (W^T Phi_J) W[J,:].  Dsh: the reduced, tril-masked
+// column blocks of Lbar, block b stored as (n - c0s[b]) x w right behind block b-1.  P: n x w, A: n x w scratch.
+int potrf_bwd_shard_f64(const double* L, int ldl, const double* W, int ldw, int n, int w, const int* c0s,
+                        int nblk, const double* Dsh, double* Gacc, double* P, double* A, cudaStream_t st) {
+  if (n <= 0 || w <= 0 || (w & 1) || nblk <= 0) return GPINV_ERR_ARG;
+  GPINV_TRY(cudaMemsetAsync(Gacc, 0, (size_t)n * n * sizeof(double), st));
+  const double* D = Dsh;
+  dim3 blk(32, 8), grd(cdiv(w, 32), cdiv(w, 8));
+  for (int b = 0; b < nblk; ++b) {
+    const int c0 = c0s[b], m = n - c0;
+    if (c0 < 0 || c0 + w > n || (c0 & 1)) return GPINV_ERR_ARG;
+    // P = L[c0:, c0:]^T D   (k >= row), then Phi on the w x w square at the top: tril, diagonal halved
+    int rc = gemm_ws(LMN, LMN, EF_BETA, m, w, m, 1.0, L + (size_t)c0 * ldl + c0, ldl, D, w, 0.0, nullptr, 0, P, w,
+                     4, st);
+    if (rc) return rc;
+    zero_upper_kernel<<<grd, blk, 0, st>>>(P, w, w);
+    GPINV_CHECK_LAUNCH();
+    scale_diag_kernel<<<cdiv(w, 256), 256, 0, st>>>(P, w, w, 0.5);
+    GPINV_CHECK_LAUNCH();
+    // A = W[c0:, :]^T Phi_J : rows above the block are dense in k, rows from c0 on have k >= row
+    if (c0 > 0) {
+      rc = gemm_ws(LMN, LMN, EF_BETA, c0, w, m, 1.0, W + (size_t)c0 * ldw, ldw, P, w, 0.0, nullptr, 0, A, w, 0, st);
+      if (rc) return rc;
+    }
+    rc = gemm_ws(LMN, LMN, EF_BETA, m, w, m, 1.0, W + (size_t)c0 * ldw + c0, ldw, P, w, 0.0, nullptr, 0,
+                 A + (size_t)c0 * w, w, 4, st);
+    if (rc) return rc;
+    // Gacc[:, :c0+w] += A W[J, :c0+w]     (W is lower triangular with an exactly zero upper part)
+    rc = gemm_ws(LK, LMN, EF_BETA, n, c0 + w, w, 1.0, A, w, W + (size_t)c0 * ldw, ldw, 1.0, Gacc, n, Gacc, n, 0, st);
+    if (rc) return rc;
+    D += (size_t)m * w;
+  }
+  return GPINV_OK;
+}
+
 }  // namespace gpinv

@@ -2,10 +2,13 @@
 
 Every rank holds the replicated state x, data and Cholesky factor; rank g evaluates the ELBO
 terms of samples [g S/G, (g+1) S/G) divided by the *global* S (sample-independent terms are
-divided by G), finishes its whole backward pass on those partial sums — the Cholesky and
-kernel reverse passes are linear in Lbar, so no intermediate exchange is needed — and the
-packed buffer [-f, -df/dx] is summed with ONE all-reduce (NCCL over NVLink on the GPUs; gloo in
-the CPU tests).  SURVEY.md 8(e).  The reference has no distributed path at all.
+divided by G) and runs the reverse pass of the sampling stage on those partial sums.  The sum over
+the ranks of [-f, -df/dx] is ONE logical all-reduce, issued in pieces so that it hides behind compute:
+the q_sqrt block (half of it: the lower triangle) as soon as the sampling stage's reverse is done,
+the small remainder at the end.  In between, the Cholesky reverse -- linear in Lbar -- is either run
+replicated on each rank's partial Lbar, or (n >= 1024, n divisible by 4G) sharded by column blocks
+after a reduce-scatter of Lbar: see ``DistContext.shard_width``.  NCCL over NVLink on the GPUs; gloo in
+the CPU tests.  SURVEY.md 8(e).  The reference has no distributed path at all.
 """
 from __future__ import annotations
 
@@ -35,6 +38,38 @@ class DistContext(object):
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
         return buf
 
+
+    # ---- column-block sharding of the Cholesky reverse pass ------------------------------------------
+    # The reverse of the factorisation is linear in Lbar; only its contraction with dK/d(lengthscale) is
+    # needed, and column block J of Phi(L^T Lbar) depends on column block J of Lbar only.  Instead of every
+    # rank reversing its own partial Lbar over the whole matrix (replicated 4/3 n^3 flops), the ranks
+    # reduce-scatter Lbar by column blocks and each reverses its blocks (about 3 n^3 / G flops).  2G blocks of
+    # width w = n / 2G, rank r owns blocks r and 2G-1-r: the triangular work is even over the ranks.
+    SHARD_MIN_N = 1024
+
+    def shard_width(self, n):
+        """Column-block width of the sharded reverse for an n x n factor, or 0 when it stays replicated."""
+        import os
+        G = self.world_size
+        env = os.environ.get("GPINV_SHARD_REVERSE")
+        if G < 2 or env == "0" or n < self.SHARD_MIN_N or n % (4 * G) != 0:
+            return 0
+        return n // (2 * G)
+
+    def shard_columns(self, n):
+        """First columns of this rank's blocks, in the order they lie in its reduce-scatter chunk."""
+        w = n // (2 * self.world_size)
+        return [self.rank * w, (2 * self.world_size - 1 - self.rank) * w]
+
+    def reduce_scatter(self, out, inp):
+        """out <- this rank's chunk of the rank-sum of inp (G equal chunks)."""
+        if dist.get_backend(self.group) == "nccl":
+            dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=self.group)
+        else:       # gloo (the CPU tests) has no reduce-scatter: sum everything, keep the own chunk
+            tmp = inp.clone()
+            dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
+            out.copy_(tmp.view(self.world_size, -1)[self.rank])
+        return out
 
     def all_reduce_async(self, buf):
         """Start the sum over ranks and return the work handle (``.wait()`` orders the caller's

@@ -56,13 +56,60 @@ class Model(Parameterized):
         ops.ensure_workspace(default_device())
 
     # ---- objective -------------------------------------------------------------------
-    def enable_cuda_graph(self, flag=True):
+    def enable_cuda_graph(self, flag=True, static_inputs=False):
         """Capture one whole evaluation (forward + hand-written backward, ~100-250 kernel launches)
         in a CUDA graph and replay it: the small configurations are launch-latency bound.  The
-        returned tensors are the graph's static outputs (valid until the next evaluation)."""
+        returned tensors are the graph's static outputs (valid until the next evaluation).
+        ``static_inputs``: the graph reads the caller's x (and eps) tensors in place instead of private
+        copies refreshed before every replay (134 MB + 8 S n bytes per evaluation at the headline size);
+        the caller updates those tensors in place and keeps passing the same ones -- a different tensor
+        gets its own capture."""
         self._use_graph = bool(flag)
+        self._static_inputs = bool(static_inputs)
         self._graphs = {}
         return self
+
+    def _graph_key(self, x, dyn):
+        key = (x.numel(),) + tuple((k, tuple(v.shape)) for k, v in sorted(dyn.items()))
+        if getattr(self, "_static_inputs", False):
+            key += (x.data_ptr(),) + tuple(v.data_ptr() for _, v in sorted(dyn.items()))
+        return key
+
+    def _graph_static(self, x, dyn):
+        """The tensors a capture reads: the caller's own (static_inputs) or private copies."""
+        if getattr(self, "_static_inputs", False):
+            return x, dict(dyn)
+        return x.detach().clone(), {k: v.detach().clone() for k, v in dyn.items()}
+
+    @staticmethod
+    def _graph_refresh(sx, sdyn, x, dyn):
+        if sx.data_ptr() != x.data_ptr():
+            sx.copy_(x)
+        for k, v in dyn.items():
+            if sdyn[k].data_ptr() != v.data_ptr():
+                sdyn[k].copy_(v)
+
+    @staticmethod
+    def _capture(fn, pool=None):
+        """Capture ``fn()`` into a new CUDA graph; returns (graph, fn's result).  Nothing but the captured
+        work may touch CUDA while the capture is open: a garbage collection that frees device or pinned
+        memory of unrelated objects in the middle of it invalidates the capture (seen when an earlier test
+        had failed and its frames were still alive), so collect first and keep the collector off until the
+        capture ends; calls of other threads (pinned-allocator event queries ...) are not checked
+        (thread_local)."""
+        import gc
+        graph = torch.cuda.CUDAGraph()
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            kw = {} if pool is None else {"pool": pool}
+            with torch.cuda.graph(graph, capture_error_mode="thread_local", **kw):
+                out = fn()
+        finally:
+            if gc_was_on:
+                gc.enable()
+        return graph, out
 
     def _graph_inputs(self, kw):
         """Tensors that vary between evaluations besides x (StVGP: the eps draws)."""
@@ -70,6 +117,8 @@ class Model(Parameterized):
 
     def _objective_device(self, x: torch.Tensor, **kw):
         """(-f, -df/dx) as CUDA tensors ([1] and [|x|]); no host synchronisation."""
+        if self.dist is not None and self.dist.world_size > 1 and self.fused_layout() is not None:
+            return self._objective_sharded(x, **kw)
         if self._use_graph:
             return self._objective_graphed(x, **kw)
         return self._objective_eager(x, **kw)
@@ -77,7 +126,7 @@ class Model(Parameterized):
     def _objective_graphed(self, x, **kw):
         self._prepare()
         dyn = self._graph_inputs(kw)
-        key = (x.numel(),) + tuple((k, tuple(v.shape)) for k, v in sorted(dyn.items()))
+        key = self._graph_key(x, dyn)
         if getattr(self, "_graph_epoch", None) != state_epoch():
             # data, a fixed value, the jitter level ... changed on the host since the capture: the
             # graph may have baked the old value (or a freed address) in.  Re-capture.
@@ -85,8 +134,7 @@ class Model(Parameterized):
             self._graph_epoch = state_epoch()
         ent = self._graphs.get(key)
         if ent is None:
-            sx = x.detach().clone()
-            sdyn = {k: v.detach().clone() for k, v in dyn.items()}
+            sx, sdyn = self._graph_static(x, dyn)
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
             side.wait_stream(cur)
@@ -98,22 +146,7 @@ class Model(Parameterized):
                     self._objective_eager(sx, reduce=False, **sdyn)
             cur.wait_stream(side)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            # Nothing but this evaluation may touch CUDA while the capture is open: a garbage
-            # collection that frees device or pinned memory of unrelated objects in the middle of
-            # it invalidates the capture (seen when an earlier test had failed and its frames were
-            # still alive), so collect now and keep the collector off until the capture ends; calls
-            # of other threads (pinned-allocator event queries ...) are not checked (thread_local).
-            import gc
-            gc.collect()
-            gc_was_on = gc.isenabled()
-            gc.disable()
-            try:
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                    f, g = self._objective_eager(sx, reduce=False, **sdyn)
-            finally:
-                if gc_was_on:
-                    gc.enable()
+            graph, (f, g) = self._capture(lambda: self._objective_eager(sx, reduce=False, **sdyn))
             # strong references to every non-input tensor the capture read (data holders, fixed
             # Params): the caching allocator must not hand their memory out while the graph lives
             keep = [d._tensor for nd in self._all_parameterized() for d in nd.data_holders] + \
@@ -121,9 +154,7 @@ class Model(Parameterized):
             ent = (graph, sx, sdyn, f, g, list(self._pending_infos), keep)
             self._graphs[key] = ent
         graph, sx, sdyn, f, g, infos, _keep = ent
-        sx.copy_(x)
-        for k, v in dyn.items():
-            sdyn[k].copy_(v)
+        self._graph_refresh(sx, sdyn, x, dyn)
         graph.replay()
         self._pending_infos = list(infos)
         if self.dist is not None:
@@ -200,18 +231,167 @@ class Model(Parameterized):
         finally:
             self.clear_tensors()
         n = x.numel()
-        if gx is None:
-            gx = torch.zeros(n, dtype=torch.float64, device=x.device)
-        st = gx.untyped_storage()
-        if gx.is_contiguous() and gx.storage_offset() == 0 and gx.numel() == n and st.nbytes() >= 8 * (n + 1):
-            # pack_grad left one slot behind the gradient: [gradient, value] without a concatenation
-            buf = torch.empty(0, dtype=torch.float64, device=x.device).set_(st, 0, (n + 1,))
-            buf[n:].copy_(nf.detach().reshape(1))
-        else:                                           # a prior contributed through a second path: summed copy
-            buf = torch.cat([gx.reshape(-1), nf.detach().reshape(1)])
+        buf = self._grad_value_buffer(gx, nf, n, x.device)
         if reduce and self.dist is not None:
             self.dist.all_reduce(buf)
         return buf[n:], buf[:n]
+
+    @staticmethod
+    def _grad_value_buffer(gx, nf, n, device):
+        """[gradient (n), value] in one buffer."""
+        if gx is None:
+            gx = torch.zeros(n + 1, dtype=torch.float64, device=device)[:n]
+        st = gx.untyped_storage()
+        if gx.is_contiguous() and gx.storage_offset() == 0 and gx.numel() == n and st.nbytes() >= 8 * (n + 1):
+            # pack_grad left one slot behind the gradient: [gradient, value] without a concatenation
+            buf = torch.empty(0, dtype=torch.float64, device=device).set_(st, 0, (n + 1,))
+            buf[n:].copy_(nf.detach().reshape(1))
+        else:                                           # a prior contributed through a second path: summed copy
+            buf = torch.cat([gx.reshape(-1), nf.detach().reshape(1)])
+        return buf
+
+    # ---- sample-sharded evaluation (gpinv_b200.dist.attach, G > 1) -----------------------------------
+    # Three compute stages with the NCCL exchanges between them (the stages are what a CUDA graph
+    # captures; the collectives stay outside the graphs):
+    #   A  forward pass on this rank's samples and the reverse pass down to Lbar            [compute]
+    #   x1 reduce-scatter of Lbar by column blocks; all-reduce of the q_sqrt gradient's lower
+    #      triangle STARTS (NCCL stream)                                                    [NVLink]
+    #   B  Cholesky reverse of this rank's column blocks -> lengthscale gradient            [compute, beside x1]
+    #   x2 all-reduce of the small remainder [hyperparameters, q_mu, value]; join x1        [NVLink]
+    #   C  the reduced pieces go back into the [gradient, value] buffer                     [compute]
+    def _shard_stage_a(self, x, kw, st):
+        from . import ops
+        ctx = self.dist
+        leaf = self.make_tensors_fused(x)
+        self._pending_infos = []
+        col = ops.DeferredReverse(lambda nn: ctx.shard_width(nn) > 0)
+        prev = ops.defer_reverse(col)
+        try:
+            with self.tensor_mode():
+                f = self.build_likelihood(**kw)
+                prior = self.build_prior()
+                if prior is not None:
+                    f = f + prior / ctx.world_size
+            nf = -f.reshape(())
+            (gx,) = torch.autograd.grad(nf, [leaf], retain_graph=True, allow_unused=True)
+        finally:
+            ops.defer_reverse(prev)
+            self.clear_tensors()
+        n = x.numel()
+        buf = self._grad_value_buffer(gx, nf, n, x.device)
+        st.update(leaf=leaf, buf=buf, n=n, items=col.items, big=None, early=None, tri=0)
+        if col.items:
+            ops.trtri_side_join()            # (inside a capture: the side stream must be joined before it ends)
+        G = ctx.world_size
+        st["rs_in"] = [ops.lbar_pack(it[5], G) for it in col.items]
+        st["rs_out"] = [torch.empty(r.numel() // G, dtype=torch.float64, device=x.device) for r in st["rs_in"]]
+        params, offs, _codes = self.fused_layout()
+        big = max(range(len(params)), key=lambda i: params[i].size)
+        a, b = offs[big], offs[big + 1]
+        if b - a >= (1 << 16):
+            nq = getattr(params[big], "_tril_rows", None)
+            st["big"] = (a, b)
+            if nq is not None and nq * nq == b - a:
+                # only tril(q_sqrt) enters the model: its gradient's strict upper part is exactly zero
+                st["tri"] = nq
+                st["early"] = ops.tri_compact(buf[a:b].view(nq, nq))
+            else:
+                st["early"] = buf[a:b]
+
+    def _shard_exchange_1(self, st):
+        ctx = self.dist
+        for o, i in zip(st["rs_out"], st["rs_in"]):
+            ctx.reduce_scatter(o, i)
+        st["work"] = ctx.all_reduce_async(st["early"]) if st["big"] is not None else None
+
+    def _shard_stage_b(self, st):
+        from . import ops
+        ctx = self.dist
+        leaf, buf, n = st["leaf"], st["buf"], st["n"]
+        gx2 = None
+        if st["items"]:
+            outs, gs = [], []
+            for (X, ls, mode, L, W, _lbar), dsh in zip(st["items"], st["rs_out"]):
+                nn = L.shape[0]
+                g = ops.chol_core_bwd_shard(X, ls, mode, L, W, dsh, ctx.shard_width(nn), ctx.shard_columns(nn))
+                outs.append(ls)
+                gs.append(g.reshape(ls.shape))
+            (gx2,) = torch.autograd.grad(outs, [leaf], grad_outputs=gs, allow_unused=True)
+        a, b = st["big"] if st["big"] is not None else (n, n)
+        small = torch.cat([buf[:a], buf[b:]])                  # ..., value last
+        if gx2 is not None:
+            small[:a + n - b] += torch.cat([gx2[:a], gx2[b:n]])
+        st["small"] = small
+
+    def _shard_exchange_2(self, st):
+        self.dist.all_reduce(st["small"])
+        if st.get("work") is not None:
+            st["work"].wait()                # stream-orders the early all-reduce before stage C
+            st["work"] = None
+
+    def _shard_stage_c(self, st):
+        from . import ops
+        buf, n, small = st["buf"], st["n"], st["small"]
+        a, b = st["big"] if st["big"] is not None else (n, n)
+        buf[:a].copy_(small[:a])
+        buf[b:].copy_(small[a:])
+        if st["tri"]:
+            ops.tri_expand_(st["early"], buf[a:b].view(st["tri"], st["tri"]))
+        return buf[n:], buf[:n]
+
+    def _objective_sharded(self, x, **kw):
+        """(-f, -df/dx) summed over the ranks; every rank gets the full result."""
+        self._prepare()
+        if not self._use_graph:
+            st = {}
+            self._shard_stage_a(x, kw, st)
+            self._shard_exchange_1(st)
+            self._shard_stage_b(st)
+            self._shard_exchange_2(st)
+            return self._shard_stage_c(st)
+        dyn = self._graph_inputs(kw)
+        key = ("sharded",) + self._graph_key(x, dyn)
+        if getattr(self, "_graph_epoch", None) != state_epoch():
+            self._graphs = {}
+            self._graph_epoch = state_epoch()
+        ent = self._graphs.get(key)
+        if ent is None:
+            sx, sdyn = self._graph_static(x, dyn)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):      # warm-up (every rank runs the same collectives in the same order)
+                    w = {}
+                    self._shard_stage_a(sx, sdyn, w)
+                    self._shard_exchange_1(w)
+                    self._shard_stage_b(w)
+                    self._shard_exchange_2(w)
+                    self._shard_stage_c(w)
+                del w
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            st = {}
+            gA, _ = self._capture(lambda: self._shard_stage_a(sx, sdyn, st))
+            self._shard_exchange_1(st)          # (on not-yet-computed buffers: keeps the ranks' NCCL order aligned)
+            gB, _ = self._capture(lambda: self._shard_stage_b(st), pool=gA.pool())
+            self._shard_exchange_2(st)
+            gC, (f, g) = self._capture(lambda: self._shard_stage_c(st), pool=gA.pool())
+            for k in ("leaf", "items"):         # the autograd graph is not needed to replay
+                st[k] = None
+            keep = [d._tensor for nd in self._all_parameterized() for d in nd.data_holders] + \
+                   [p._fixed_dev for p in self.all_params() if p.fixed]
+            ent = (gA, gB, gC, sx, sdyn, st, f, g, list(self._pending_infos), keep)
+            self._graphs[key] = ent
+        gA, gB, gC, sx, sdyn, st, f, g, infos, _keep = ent
+        self._graph_refresh(sx, sdyn, x, dyn)
+        gA.replay()
+        self._shard_exchange_1(st)
+        gB.replay()
+        self._shard_exchange_2(st)
+        gC.replay()
+        self._pending_infos = list(infos)
+        return f, g
 
     def _check_infos(self):
         infos, self._pending_infos = self._pending_infos, []
@@ -456,6 +636,12 @@ class Model(Parameterized):
         params[big]._before_use = wait_big
         leaves[big].register_hook(big_grad_hook)
         self._pending_infos = []
+        from . import ops
+        col = None
+        if self.dist is not None and self.dist.world_size > 1:
+            # sample sharding: the Cholesky reverse waits for the reduce-scatter of Lbar (see _shard_stage_a)
+            col = ops.DeferredReverse(lambda nn: self.dist.shard_width(nn) > 0)
+        prev = ops.defer_reverse(col)
         try:
             with self.tensor_mode():
                 f = self.build_likelihood(**kw)
@@ -464,8 +650,23 @@ class Model(Parameterized):
                     f = f + (prior if self.dist is None else prior / self.dist.world_size)
             nf = -f.reshape(())
             tr("forward_issued")
-            grads = torch.autograd.grad(nf, leaves, allow_unused=True)
+            grads = torch.autograd.grad(nf, leaves, allow_unused=True, retain_graph=col is not None)
+            if col is not None and col.items:
+                ctx = self.dist
+                ops.trtri_side_join()
+                outs, gs = [], []
+                for (X_, ls_, mode_, L_, W_, lbar_) in col.items:
+                    nn = L_.shape[0]
+                    rs_in = ops.lbar_pack(lbar_, ctx.world_size)
+                    rs_out = torch.empty(rs_in.numel() // ctx.world_size, dtype=torch.float64, device=dev)
+                    ctx.reduce_scatter(rs_out, rs_in)
+                    g_ = ops.chol_core_bwd_shard(X_, ls_, mode_, L_, W_, rs_out, ctx.shard_width(nn), ctx.shard_columns(nn))
+                    outs.append(ls_)
+                    gs.append(g_.reshape(ls_.shape))
+                extra = torch.autograd.grad(outs, leaves, grad_outputs=gs, allow_unused=True)
+                grads = tuple(g if e is None else (e if g is None else g + e) for g, e in zip(grads, extra))
         finally:
+            ops.defer_reverse(prev)
             params[big]._before_use = None
             self.clear_tensors()
             th.join()

@@ -257,10 +257,88 @@ def _chol_core_setup(ctx, inputs, output):
     ctx.ls_shape = ls.shape
 
 
+class DeferredReverse(object):
+    """Collector for the sample-sharded evaluation (gpinv_b200/dist.py): while one is installed with
+    ``defer_reverse``, the reverse pass of every factorisation it accepts is NOT run where autograd reaches
+    it -- (X, ls, mode, L, W, Lbar) is recorded instead and the lengthscales receive no gradient -- so that
+    the caller can exchange Lbar between the ranks first and run ``chol_core_bwd_shard`` afterwards."""
+
+    def __init__(self, accepts):
+        self.accepts = accepts
+        self.items = []
+
+
+_DEFER = None
+
+
+def defer_reverse(collector):
+    """Install (or, with None, remove) the collector; returns the previous one."""
+    global _DEFER
+    prev, _DEFER = _DEFER, collector
+    return prev
+
+
 def _chol_core_backward(ctx, Lbar, _info_bar, _w_bar):
     X, ls, L, W = ctx.saved_tensors
+    d = _DEFER
+    if d is not None and W.numel() and d.accepts(L.shape[0]):
+        d.items.append((X, ls, ctx.mode, L, W, Lbar.contiguous()))
+        return None, None, None, None, None
     g = chol_core_bwd(X, ls, ctx.mode, L, Lbar.contiguous(), W)
     return None, g.reshape(ctx.ls_shape), None, None, None
+
+
+def trtri_side_join():
+    """Order the current stream after the side-stream inversion started by ``chol_core(with_inverse=True)``."""
+    _capi.check(_capi.lib().gpinv_trtri_side_join(_st()), "trtri_side_join")
+
+
+def lbar_pack(Lbar: Tensor, G: int) -> Tensor:
+    """tril(Lbar) regrouped into the reduce-scatter input of the column-block sharded reverse: G chunks of
+    (n + w) w entries, w = n / 2G, chunk r = column blocks r and 2G-1-r from their diagonal down."""
+    Lbar = _chk(Lbar, "Lbar")
+    n = Lbar.shape[0]
+    w = n // (2 * G)
+    out = torch.empty(G * (n + w) * w, dtype=torch.float64, device=Lbar.device)
+    _capi.check(_capi.lib().gpinv_lbar_pack_f64(_p(Lbar), n, n, w, G, _p(out), _st()), "lbar_pack")
+    return out
+
+
+def chol_core_bwd_shard(X: Tensor, ls: Tensor, mode: int, L: Tensor, W: Tensor, Dsh: Tensor, w: int,
+                        c0s: List[int]) -> Tensor:
+    """This rank's share of dObj/d(lengthscales): the reverse of its column blocks (first columns ``c0s``,
+    width ``w``) of the rank-summed tril(Lbar), ``Dsh`` = its reduce-scatter output.  The caller has joined
+    the side stream that built W = L^-1 (``trtri_side_join``)."""
+    X = _chk(X, "X")
+    ls = _chk(ls, "ls").reshape(-1)
+    L = _chk(L, "L")
+    Dsh = _chk(Dsh, "Dsh")
+    n, D = X.shape
+    ard = 1 if ls.numel() > 1 else 0
+    out = torch.empty_like(ls)
+    lib = _capi.lib()
+    ws = _ws(lib.gpinv_chol_core_bwd_ws_bytes(n, D), X)
+    c0 = (C.c_int * len(c0s))(*c0s)
+    rc = lib.gpinv_chol_core_bwd_shard_f64(_p(X), n, D, D, _p(ls), ard, mode, _p(L), n, _p(W), _p(Dsh), w, c0,
+                                           len(c0s), _p(out), _p(ws), _st())
+    _capi.check(rc, "chol_core_bwd_shard")
+    return out
+
+
+def tri_compact(M: Tensor) -> Tensor:
+    """Lower triangle of the n x n matrix ``M`` as n (n + 1) / 2 packed entries."""
+    M = _chk(M, "M")
+    n = M.shape[0]
+    out = torch.empty(n * (n + 1) // 2, dtype=torch.float64, device=M.device)
+    _capi.check(_capi.lib().gpinv_tri_compact_f64(_p(M), n, n, _p(out), _st()), "tri_compact")
+    return out
+
+
+def tri_expand_(src: Tensor, M: Tensor) -> Tensor:
+    """Write the packed lower triangle ``src`` into the lower triangle of ``M`` (the rest is left alone)."""
+    n = M.shape[0]
+    _capi.check(_capi.lib().gpinv_tri_expand_f64(_p(src), _p(M), n, n, _st()), "tri_expand")
+    return M
 
 
 chol_core.register_autograd(_chol_core_backward, setup_context=_chol_core_setup)

@@ -222,6 +222,26 @@ int gpinv_kl_white_bwd_f64(const double* q_mu, const double* q_sqrt, int n, int 
 int gpinv_adam_step_f64(double* x, double* m, double* v, const double* g, long long count, double lr,
                         double beta1, double beta2, double epsilon, long long* step, void* stream);
 
+/* --- sample sharding over G GPUs (the reference has no distributed path).  The reverse of
+ * the Cholesky at GPinv/kernels.py:59 is linear in Lbar and only its contraction with dK/d(lengthscale) is
+ * needed: with W = L^-1, G_K = W^T Phi(L^T Lbar) W = sum over column blocks J of (W^T Phi[:,J]) W[J,:], and
+ * Phi[:,J] needs Lbar[:,J] only.  The ranks therefore reduce-scatter Lbar by column blocks of width
+ * w = n / 2G (rank r owns blocks r and 2G-1-r), reverse their own blocks, and sum the scalar results.
+ *   gpinv_lbar_pack_f64: out = G chunks of (n + w) w doubles, chunk r = [tril(Lbar)[r w:, block r] ;
+ *     tril(Lbar)[(2G-1-r) w:, block 2G-1-r]] (rows x w, row-major) -- the reduce-scatter input.
+ *   gpinv_chol_core_bwd_shard_f64: Dsh = this rank's reduced chunk, c0s (HOST) = first column of each of its
+ *     nblk blocks in chunk order, Winv = L^-1 from gpinv_trtri_side_f64 (the caller has already ordered
+ *     `stream` after it with gpinv_trtri_side_join); ls_bar <- this rank's share of dObj/d(lengthscales).
+ *     ws: gpinv_chol_core_bwd_ws_bytes(n, D).
+ *   gpinv_tri_compact_f64 / gpinv_tri_expand_f64: lower triangle of an n x n row-major matrix <-> packed
+ *     rows [i (i + 1) / 2 + c]; the q_sqrt gradient crosses NVLink in this form (half the bytes). */
+int gpinv_lbar_pack_f64(const double* Lbar, int ldlb, int n, int w, int G, double* out, void* stream);
+int gpinv_chol_core_bwd_shard_f64(const double* X, int n, int D, int ldx, const double* ls, int ard, int mode,
+                                  const double* L, int ldl, const double* Winv, const double* Dsh, int w,
+                                  const int* c0s, int nblk, double* ls_bar, void* ws, void* stream);
+int gpinv_tri_compact_f64(const double* src, int ld, int n, double* dst, void* stream);
+int gpinv_tri_expand_f64(const double* src, double* dst, int ld, int n, void* stream);
+
 /* --- reductions used by T8/T11/T17 */
 int gpinv_sumsq_f64(const double* x, size_t count, double* out, void* stream);
 

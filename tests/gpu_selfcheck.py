@@ -328,10 +328,45 @@ def check_pack():
     report("adam_step step counter", abs(int(step.item()) - 7), 0.5)
 
 
+def check_shard():
+    """Column-block sharded Cholesky reverse (multi-GPU path) on one GPU: the pack layout against its
+    numpy restatement, the triangle compaction round trip, and the sum over the ranks' shares against the
+    replicated reverse, for G = 2, 4, 8."""
+    from tests.helpers import lbar_pack_reference
+    for n, Gs in ((1024, (2, 4, 8)), (640, (2,)), (2048, (4,))):
+        x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)[:, None]
+        ls = t([0.3])
+        L, info, W = ops.chol_core(x, ls, 1, 1e-6, True)
+        rng = np.random.RandomState(n)
+        Lbar = t(rng.randn(n, n))                   # the strict upper part must be ignored
+        ref = ops.chol_core_bwd(x, ls, 1, L, Lbar, W)
+        for G in Gs:
+            w = n // (2 * G)
+            packed = ops.lbar_pack(Lbar, G)
+            report("lbar_pack n=%d G=%d" % (n, G),
+                   rel(packed, torch.tensor(lbar_pack_reference(Lbar.cpu().numpy(), G))), 0.0)
+            ops.trtri_side_join()
+            tot = torch.zeros_like(ref)
+            chunks = packed.view(G, -1)
+            for r in range(G):
+                c0s = [r * w, (2 * G - 1 - r) * w]
+                tot += ops.chol_core_bwd_shard(x, ls, 1, L, W, chunks[r].contiguous(), w, c0s)
+            report("chol_core_bwd_shard n=%d G=%d (sum of shares vs replicated)" % (n, G), rel(tot, ref), 1e-7)
+    for n in (1, 7, 300, 1024):
+        M = t(np.random.RandomState(n).randn(n, n))
+        c = ops.tri_compact(M)
+        iu = np.tril_indices(n)
+        report("tri_compact n=%d" % n, rel(c, torch.tensor(M.cpu().numpy()[iu])), 0.0)
+        Z = torch.full((n, n), 7.0, dtype=torch.float64, device=dev)
+        ops.tri_expand_(c, Z)
+        want = torch.where(torch.ones(n, n, device=dev).tril().bool(), M, torch.full_like(M, 7.0))
+        report("tri_expand n=%d" % n, rel(Z, want), 0.0)
+
+
 if __name__ == "__main__":
     t0 = time.time()
     names = sys.argv[1:] or ["check_gemm", "check_kcore", "check_potrf", "check_trsm", "check_sample", "check_kron",
-                             "check_pack", "check_liks"]
+                             "check_pack", "check_liks", "check_shard"]
     for fn in [globals()[nm] for nm in names]:
         try:
             fn()

@@ -148,3 +148,37 @@ def check_compact(f, g, d, n_hyper, f_tol, g_tol, hyper_tol):
     assert np.max(np.abs(s["g_proj"] - d["g_proj"])) <= g_tol * scale * 10
     assert np.linalg.norm(s["g_samples"] - d["g_samples"]) <= g_tol * max(np.linalg.norm(d["g_samples"]), 1e-300) * 10
     assert np.all(np.abs(s["g_hyper"] - d["g_hyper"]) <= hyper_tol * np.abs(d["g_hyper"])), (s["g_hyper"], d["g_hyper"])
+
+
+def lbar_pack_reference(Lbar, G):
+    """numpy restatement of the reduce-scatter layout of the column-block sharded Cholesky reverse
+    (include/gpinv_b200.h, gpinv_lbar_pack_f64): G chunks of (n + w) w entries, w = n / 2G; chunk r holds
+    tril(Lbar)[r w:, block r] followed by tril(Lbar)[(2G-1-r) w:, block 2G-1-r], rows x w, row-major."""
+    n = Lbar.shape[0]
+    w = n // (2 * G)
+    T = np.tril(Lbar)
+    out = []
+    for r in range(G):
+        for b in (r, 2 * G - 1 - r):
+            out.append(T[b * w:, b * w:(b + 1) * w].reshape(-1))
+    return np.concatenate(out)
+
+
+def shard_reverse_reference(L, chunk, c0s, w, dK):
+    """numpy restatement of one rank's share of <G_K, dK>, G_K = W^T Phi(L^T Lbar) W, from its reduced
+    chunk of column blocks (first columns c0s, width w): sum over its blocks J of <(W^T Phi[:,J]) W[J,:], dK>."""
+    n = L.shape[0]
+    W = np.linalg.inv(L)
+    total, o = 0.0, 0
+    for c0 in c0s:
+        m = n - c0
+        D = chunk[o:o + m * w].reshape(m, w)
+        o += m * w
+        P = L[c0:, c0:].T @ D                       # rows c0.. of L^T Lbar[:, J]
+        sq = np.tril(P[:w])
+        sq[np.diag_indices(w)] *= 0.5
+        P[:w] = sq                                  # Phi: lower part, diagonal halved
+        A = W[c0:, :].T @ P                         # n x w
+        Gk = A @ W[c0:c0 + w, :]                    # n x n
+        total += float(np.sum(Gk * dK))
+    return total

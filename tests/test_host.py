@@ -265,6 +265,59 @@ def test_sample_sharding_world_size_2_gloo(tmp_path):
     assert codes == [0, 0], codes
 
 
+_SHARD_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from gpinv_b200.dist import DistContext
+from tests.helpers import lbar_pack_reference, shard_reverse_reference
+rank, world = int(sys.argv[2]), int(sys.argv[3])
+os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = sys.argv[4]
+dist.init_process_group("gloo", rank=rank, world_size=world)
+ctx = DistContext()
+ctx.SHARD_MIN_N = 16
+n = 48
+assert ctx.shard_width(n) == n // (2 * world) and ctx.shard_width(n + 2) == 0
+rng = np.random.RandomState(0)                       # the same on every rank: L, dK
+x = np.sort(rng.rand(n))
+K = np.exp(-0.5 * (x[:, None] - x[None, :]) ** 2 / 0.1 ** 2) + 1e-3 * np.eye(n)
+L = np.linalg.cholesky(K)
+dK = rng.randn(n, n); dK = dK + dK.T
+Lbar_r = np.random.RandomState(10 + rank).randn(n, n)      # this rank's partial dObj/dL
+# exchange 1: reduce-scatter of the packed column blocks
+w = ctx.shard_width(n)
+inp = torch.from_numpy(lbar_pack_reference(Lbar_r, world))
+out = torch.empty(inp.numel() // world, dtype=torch.float64)
+ctx.reduce_scatter(out, inp)
+share = shard_reverse_reference(L, out.numpy(), ctx.shard_columns(n), w, dK)
+tot = torch.tensor([share], dtype=torch.float64)
+ctx.all_reduce(tot)
+# replicated formula on the rank-summed Lbar
+Lbar = sum(np.random.RandomState(10 + r).randn(n, n) for r in range(world))
+P = np.tril(L.T @ np.tril(Lbar)); P[np.diag_indices(n)] *= 0.5
+W = np.linalg.inv(L)
+S = W.T @ P @ W
+want = float(np.sum(0.5 * (S + S.T) * dK))
+ok = abs(float(tot) - want) <= 1e-10 * abs(want)
+if not ok:
+    print("rank %d: sharded %r replicated %r" % (rank, float(tot), want), flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 3)
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_column_block_sharded_cholesky_reverse_gloo(tmp_path, world):
+    """Host-side logic of the sharded Cholesky reverse (gpinv_b200/dist.py): block assignment, the
+    reduce-scatter layout and the sum of the ranks' shares reproduce the replicated formula."""
+    script = tmp_path / "shard_worker.py"
+    script.write_text(_SHARD_WORKER)
+    port = str(33000 + os.getpid() % 2000 + world)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), str(world), port]) for r in range(world)]
+    codes = [p.wait(timeout=300) for p in procs]
+    assert codes == [0] * world, codes
+
+
 def test_los_generators_match_the_loop_restatement():
     from gpinv_b200 import los
     r, z = np.linspace(0, 1, 30), np.linspace(-0.9, 0.9, 40)

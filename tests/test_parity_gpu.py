@@ -774,6 +774,8 @@ eps = np.random.RandomState(3).randn(1, S, n)
 f0, g0 = m._objective(x, eps=eps)                                 # single rank, all samples
 g0 = g0.copy()
 gdist.attach(m)
+m.dist.SHARD_MIN_N = 512         # n = 640: the Cholesky reverse runs sharded by column blocks (w = 160)
+assert m.dist.shard_width(n) == 160
 ok = True
 
 
