@@ -199,7 +199,26 @@ def _time_events(fn, reps, warm=3):
     return a.elapsed_time(b) / reps / 1e3
 
 
-def roofline_section(m, x, eps, n, M, S, world, t_eval, args, dev):
+def insitu_abel_seconds(m, x, eps):
+    """Duration of the forward Abel op inside eager evaluations (CUDA events around the op on the launching
+    stream).  The evaluation contains the collectives of the sample sharding: EVERY rank calls this."""
+    import torch
+    from gpinv_b200 import ops
+    ops.TIMERS = {}
+    was_graph = m._use_graph
+    m._use_graph = False
+    try:
+        for _ in range(3):
+            m._objective_device(x, eps=eps)
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) / 1e3 for a, b in ops.TIMERS.get("abel_resid", [])]
+    finally:
+        ops.TIMERS = None
+        m._use_graph = was_graph
+    return float(np.mean(ts[1:])) if len(ts) > 1 else None
+
+
+def roofline_section(m, x, eps, n, M, S, world, t_eval, args, dev, t_insitu):
     """Roofline of the dominant kernel (Abel-transform DMMA GEMM) measured two ways -- inside one
     eager evaluation (CUDA events around the op on the launching stream) and alone in a loop --
     plus the denominators measured in the same process: cuBLAS DGEMM 8192^3 burst and 4 s
@@ -212,19 +231,6 @@ def roofline_section(m, x, eps, n, M, S, world, t_eval, args, dev):
     Am = m.likelihood.Amat.tensor()
     Ym = m.Y.tensor().reshape(-1).contiguous()
     t_alone = _time_events(lambda: ops.abel_resid(Fm, Xm, Am, Ym), 10)
-    # in situ: one eager evaluation with events around the forward Abel op
-    ops.TIMERS = {}
-    was_graph = m._use_graph
-    m._use_graph = False
-    try:
-        for _ in range(3):
-            m._objective_device(x, eps=eps)
-        torch.cuda.synchronize()
-        ts = [a.elapsed_time(b) / 1e3 for a, b in ops.TIMERS.get("abel_resid", [])]
-    finally:
-        ops.TIMERS = None
-        m._use_graph = was_graph
-    t_insitu = float(np.mean(ts[1:])) if len(ts) > 1 else None
     flops = 2.0 * Sl * n * M
 
     # ---- denominators, same process ----
@@ -427,8 +433,9 @@ def main():
 
     # ---- dominant kernel roofline: the DMMA GEMM of the Abel transform ----
     roof, denominators, hbm_stages = None, None, None
+    t_insitu = insitu_abel_seconds(m, x, eps)
     if rank == 0:
-        roof, denominators, hbm_stages = roofline_section(m, x, eps, n, M, S, world, t_dev / K, args, dev)
+        roof, denominators, hbm_stages = roofline_section(m, x, eps, n, M, S, world, t_dev / K, args, dev, t_insitu)
 
     # kernel launches of one evaluation, counted with torch's CUDA profiler.  The evaluation
     # contains the all-reduce, so EVERY rank runs it; rank 0 reports.

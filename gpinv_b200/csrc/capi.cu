@@ -244,19 +244,19 @@ size_t gpinv_chol_core_bwd_ws_bytes(int n, int D) {
 int gpinv_chol_core_bwd_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
                             int mode, const double* L, int ldl, const double* Lbar, int ldlb,
                             double* ls_bar, void* ws, void* stream) {
-  return gpinv_chol_core_bwd2_f64(X, n, D, ldx, ls, ard, mode, L, ldl, Lbar, ldlb, nullptr, ls_bar, ws, stream);
+  return gpinv_chol_core_bwd2_f64(X, n, D, ldx, ls, ard, mode, L, ldl, Lbar, ldlb, nullptr, 0, ls_bar, ws, stream);
 }
 
 int gpinv_chol_core_bwd2_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
                              int mode, const double* L, int ldl, const double* Lbar, int ldlb,
-                             const double* Winv, double* ls_bar, void* ws, void* stream) {
+                             const double* Winv, int winv_ready, double* ls_bar, void* ws, void* stream) {
   if (n <= 0 || D <= 0 || ldl < n || ldlb < n) return GPINV_ERR_ARG;
   double* Ab = static_cast<double*>(ws);              // n x n: tril(Lbar), then the Murray-lower Kbar
   double* sweep_ws = Ab + (size_t)n * n;              // potrf_bwd_inv_ws_bytes(n)
   double* kws = sweep_ws + potrf_bwd_inv_ws_bytes(n) / sizeof(double);
   int rc = tril_copy_f64(Lbar, ldlb, Ab, n, n, ST(stream));
   if (rc) return rc;
-  if (Winv) {
+  if (Winv && !winv_ready) {
     rc = trtri_side_join_f64(ST(stream));
     if (rc) return rc;
   }

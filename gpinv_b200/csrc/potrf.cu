@@ -449,12 +449,23 @@ int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaSt
   bool side_pending = false;
   for (int o = 0; o < n; o += NBO) {
     const int w = min(NBO, n - o);
+    // Inside an outer panel the 64-column sub-panels are brought up to date either right-looking (after
+    // sub-panel j: update ALL remaining columns of the outer panel, K = 64) or left-looking (before
+    // sub-panel j: update ITS 64 columns with everything finished in this outer panel, K = 64 j).  Both are
+    // latency-bound launches on the critical chain; the left-looking ones are narrower (N = 64).
+    static const bool inner_left = (getenv("GPINV_POTRF_INNER_LEFT") != nullptr);
     for (int i = o; i < o + w; i += NB) {
       const int b = min(NB, o + w - i);
       const int below = n - i - b;
+      if (inner_left && i > o) {
+        double* P = A + (size_t)i * lda + o;
+        rc = gemm_simple(LK, LK, n - i, b, i - o, -1.0, P, lda, P, lda, 1.0, A + (size_t)i * lda + i, lda, false,
+                         0, 1, st);
+        if (rc) return rc;
+      }
       panel_kernel<<<max(1, cdiv(below, RB)), 2 * (NB + RB), PANEL_SMEM, st>>>(A, lda, n, i, b, info);
       GPINV_CHECK_LAUNCH();
-      if (i + b < o + w) {
+      if (!inner_left && i + b < o + w) {
         double* P = A + (size_t)(i + b) * lda + i;
         rc = gemm_simple(LK, LK, n - (i + b), o + w - (i + b), b, -1.0, P, lda, P, lda, 1.0,
                          A + (size_t)(i + b) * lda + (i + b), lda, false, 0, 1, st);

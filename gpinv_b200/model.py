@@ -415,8 +415,12 @@ class Model(Parameterized):
             self._out_pool = []
         hout, finish = self._result_buffer(n)
         if n >= self.OVERLAP_MIN:
-            # large states: the transfers are pipelined against the evaluation (eager launches:
-            # the upload must be able to slot in between the Cholesky and the sampling stage)
+            # large states: the transfers are pipelined against the evaluation, which is replayed from
+            # CUDA graphs cut where the transfers slot in (enable_cuda_graph) or launched eagerly
+            if self._use_graph:
+                out = self._objective_host_pipeline(x, hin, hout, finish, dev, **kw)
+                if out is not None:
+                    return out
             return self._objective_host_overlapped(x, hin, hout, finish, dev, **kw)
         # torch's CPU copy is multi-threaded; a plain numpy assignment of 134 MB is not
         hout._gpinv_fresh_zero = False
@@ -469,6 +473,7 @@ class Model(Parameterized):
         return hout, finish
 
     OVERLAP_MIN = 1 << 21     # elements of x above which the host path pipelines its transfers
+    DEFER_MIN_N = 1024        # factor size from which the graph-replayed host path cuts before the Cholesky reverse
 
     def _objective_host_overlapped(self, x, hin, hout, finish, dev, **kw):
         """Host API for large states (the 134 MB x / gradient of the headline config): the
@@ -698,6 +703,252 @@ class Model(Parameterized):
             print("e2e-trace " + " ".join("%s=%.2f" % (k, 1e3 * (v - trace[0][1])) for k, v in trace),
                   file=sys.stderr)
         return out
+
+    # ---- host API, large states, graph replay ------------------------------------------------------
+    # One evaluation = three CUDA graphs, cut where the host transfers (and, under sample sharding, the
+    # NCCL exchanges) slot in:
+    #   G1  small parameter blocks -> kernel build, Cholesky, L^-1              ||  q_sqrt upload (copy stream)
+    #   G2  sampling stage, likelihood, their reverse pass  -> Qbar, Lbar
+    #   G3  Cholesky reverse -> hyperparameter gradients                        ||  Qbar download (copy stream)
+    # The cut between G1 and G2 is made from the callback that fires when q_sqrt is first read; the cut
+    # between G2 and G3 uses the deferred reverse of ops.DeferredReverse.
+    def _objective_host_pipeline(self, x, hin, hout, finish, dev, **kw):
+        from . import ops, _capi
+        self._prepare()
+        n = x.size
+        params = [p for p in self.all_params() if not p.fixed]
+        offs, o = [], 0
+        for p in params:
+            offs.append((o, o + p.size))
+            o += p.size
+        big = max(range(len(params)), key=lambda i: params[i].size)
+        b0, b1 = offs[big]
+        nq = params[big]._tril_rows
+        if nq is None or nq * nq != b1 - b0 or nq < 512 or params[big].prior is not None:
+            return None
+        eps_given = kw.get("eps") is not None
+        key = ("host", n, tuple(np.shape(kw["eps"])) if eps_given else None)
+        if getattr(self, "_graph_epoch", None) != state_epoch():
+            self._graphs = {}
+            self._graph_epoch = state_epoch()
+        ent = self._graphs.get(key)
+        if ent is None:
+            warm = self.__dict__.setdefault("_host_warm", {})
+            if warm.get(key, 0) < 2:          # the eager pipelined path warms up plans, workspaces, NCCL
+                warm[key] = warm.get(key, 0) + 1
+                return None
+            ent = self._host_pipeline_capture(n, params, offs, big, nq, self._graph_inputs(kw), dev)
+            self._graphs[key] = ent
+        st = ent
+        ctx = st["ctx"]
+        cur = torch.cuda.current_stream()
+        cs = st["cs"]
+        xt = torch.from_numpy(x)
+        h2d = d2h = 0
+        for a, b, d in ((0, b0, 0), (b1, n, b0)):           # small blocks: on the compute stream
+            if b > a:
+                hin[a:b].copy_(xt[a:b])
+                st["xd"][d:d + b - a].copy_(hin[a:b], non_blocking=True)
+                h2d += 8 * (b - a)
+        if eps_given:
+            e = kw["eps"]
+            if not isinstance(e, torch.Tensor):
+                e = torch.as_tensor(np.ascontiguousarray(e, dtype=np.float64))
+            st["sdyn"]["eps"].copy_(e, non_blocking=True)
+        else:
+            self._refill_graph_inputs(st["sdyn"])
+        st["g1"].replay()
+        # q_sqrt: lower trapezoids of 16 row blocks, gathered into pinned memory and sent block by block by
+        # one native call while G1 runs; under sample sharding every rank sends 1/G of the blocks and one
+        # all-reduce over NVLink completes the packed buffer everywhere
+        with torch.cuda.stream(cs):
+            if ctx is not None:
+                st["dstage"].zero_()
+            nthr = max(1, min(8, torch.get_num_threads()))
+            rc = _capi.lib().gpinv_upload_tril_blocks_f64(
+                x.ctypes.data + 8 * b0, nq, st["rb"], hin.data_ptr() + 8 * b0, st["dstage"].data_ptr(),
+                st["offs_np"].ctypes.data, st["take_np"].ctypes.data, len(st["blocks"]), nthr, cs.cuda_stream)
+            _capi.check(rc, "upload_tril_blocks")
+            h2d += st["h2d_big"]
+            if ctx is not None:
+                ctx.all_reduce(st["dstage"])
+            dst2 = st["xbig"].view(nq, nq)
+            for r0, r1, o_ in st["blocks"]:
+                dst2[r0:r1, :r1].copy_(st["dstage"][o_:o_ + (r1 - r0) * r1].view(r1 - r0, r1))
+            st["ev_up"].record(cs)
+        cur.wait_event(st["ev_up"])
+        st["g2"].replay()
+        work = None
+        if ctx is not None:
+            for o_, i_ in zip(st["rs_out"], st["rs_in"]):
+                ctx.reduce_scatter(o_, i_)
+            work = ctx.all_reduce_async(st["qc"])
+        st["ev_q"].record(cur)
+        gb = st["gb"]
+        with torch.cuda.stream(cs):
+            cs.wait_event(st["ev_q"])
+            if work is not None:
+                work.wait()
+                ops.tri_expand_(st["qc"], gb)
+            tri_only = getattr(hout, "_gpinv_fresh_zero", False) or getattr(hout, "_gpinv_upper_zero", None) == (b0, nq)
+            if tri_only:
+                for r0, r1, _ in st["blocks"]:
+                    off = 8 * (r0 * nq)
+                    _capi.check(_capi.lib().gpinv_memcpy2d_async(
+                        hout.data_ptr() + 8 * (1 + b0) + off, 8 * nq, gb.data_ptr() + off, 8 * nq,
+                        8 * r1, r1 - r0, 2, cs.cuda_stream), "memcpy2d")
+                    d2h += 8 * r1 * (r1 - r0)
+                hout._gpinv_upper_zero = (b0, nq)
+            else:
+                hout._gpinv_upper_zero = None
+                hout[1 + b0:1 + b1].copy_(gb.reshape(-1), non_blocking=True)
+                d2h += 8 * (b1 - b0)
+            hout._gpinv_fresh_zero = False
+        st["g3"].replay()
+        small = st["small"]
+        if ctx is not None:
+            ctx.all_reduce(small)
+        hout[:1].copy_(small[:1], non_blocking=True)
+        o = 1
+        for i, (a, b) in enumerate(offs):
+            if i != big:
+                hout[1 + a:1 + b].copy_(small[o:o + b - a], non_blocking=True)
+                o += b - a
+        d2h += 8 * small.numel()
+        cur.synchronize()
+        cs.synchronize()
+        self._pending_infos = list(st["infos"])
+        self._check_infos()
+        self._last_h2d_bytes, self._last_d2h_bytes = h2d, d2h
+        return finish()
+
+    def _host_pipeline_capture(self, n, params, offs, big, nq, dyn, dev):
+        import gc
+        from . import ops
+        ctx = self.dist if (self.dist is not None and self.dist.world_size > 1) else None
+        G = 1 if ctx is None else ctx.world_size
+        rank = 0 if ctx is None else ctx.rank
+        b0, b1 = offs[big]
+        st = {"ctx": ctx}
+        st["xd"] = torch.zeros(n - (b1 - b0), dtype=torch.float64, device=dev)
+        st["xbig"] = torch.zeros(b1 - b0, dtype=torch.float64, device=dev)
+        rb = -(-nq // 16)
+        blocks, o = [], 0
+        for r0 in range(0, nq, rb):
+            r1 = min(nq, r0 + rb)
+            blocks.append((r0, r1, o))
+            o += (r1 - r0) * r1
+        st["rb"], st["blocks"] = rb, blocks
+        st["dstage"] = torch.zeros(o, dtype=torch.float64, device=dev)
+        order = sorted(range(len(blocks)), key=lambda k: -blocks[k][2])
+        mine = set(k for j, k in enumerate(order) if j % G == rank)
+        st["offs_np"] = np.array([o_ for _, _, o_ in blocks], dtype=np.int64)
+        st["take_np"] = np.array([1 if k in mine else 0 for k in range(len(blocks))], dtype=np.int32)
+        st["h2d_big"] = sum(8 * (r1 - r0) * r1 for k, (r0, r1, _) in enumerate(blocks) if k in mine)
+        st["sdyn"] = sdyn = {k: v.detach().clone() for k, v in dyn.items()}
+        st["cs"] = self._copy_stream if getattr(self, "_copy_stream", None) is not None else torch.cuda.Stream()
+        self._copy_stream = st["cs"]
+        st["ev_up"], st["ev_q"] = torch.cuda.Event(), torch.cuda.Event()
+        accept = (lambda nn: ctx.shard_width(nn) > 0) if ctx is not None else (lambda nn: nn >= self.DEFER_MIN_N)
+        col = ops.DeferredReverse(accept)
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        mode = {"capture_error_mode": "thread_local"}
+
+        def cut_1():
+            # first read of q_sqrt: everything captured so far does not depend on the upload
+            if ops.SIDE_PENDING[0]:
+                ops.trtri_side_join()
+            g1.capture_end()
+            g2.capture_begin(pool=g1.pool(), **mode)
+            active[0] = g2
+
+        active = [None]
+        torch.cuda.synchronize()
+        cap = torch.cuda.Stream()
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        prev = ops.defer_reverse(col)
+        try:
+            with torch.cuda.stream(cap):
+                g1.capture_begin(**mode)
+                active[0] = g1
+                leaves = self.make_tensors(st["xd"], override={big: st["xbig"]})
+                params[big]._before_use = cut_1
+                self._pending_infos = []
+                with self.tensor_mode():
+                    f = self.build_likelihood(**sdyn)
+                    prior = self.build_prior()
+                    if prior is not None:
+                        f = f + (prior if ctx is None else prior / G)
+                if params[big]._before_use is not None:
+                    raise RuntimeError("the largest parameter block was never read by build_likelihood")
+                nf = -f.reshape(())
+                grads = torch.autograd.grad(nf, leaves, retain_graph=True, allow_unused=True)
+                gb = grads[big].reshape(nq, nq)
+                if not gb.is_contiguous():
+                    gb = gb.contiguous()
+                st["gb"] = gb
+                if ctx is not None:
+                    st["rs_in"] = [ops.lbar_pack(it[5], G) for it in col.items]
+                    st["rs_out"] = [torch.empty(r.numel() // G, dtype=torch.float64, device=dev) for r in st["rs_in"]]
+                    st["qc"] = ops.tri_compact(gb)
+                g2.capture_end()
+                active[0] = None
+                if ctx is not None:             # the ranks' NCCL call order stays aligned with the replay's
+                    ctx.all_reduce(st["dstage"])
+                    for o_, i_ in zip(st["rs_out"], st["rs_in"]):
+                        ctx.reduce_scatter(o_, i_)
+                    ctx.all_reduce(st["qc"])
+                g3.capture_begin(pool=g1.pool(), **mode)
+                active[0] = g3
+                extra = None
+                if col.items:
+                    outs, gs = [], []
+                    for k, (X_, ls_, mode_, L_, W_, lbar_) in enumerate(col.items):
+                        if ctx is not None:
+                            nn = L_.shape[0]
+                            g_ = ops.chol_core_bwd_shard(X_, ls_, mode_, L_, W_, st["rs_out"][k], ctx.shard_width(nn),
+                                                         ctx.shard_columns(nn))
+                        else:
+                            g_ = ops.chol_core_bwd(X_, ls_, mode_, L_, lbar_, W_, True)
+                        outs.append(ls_)
+                        gs.append(g_.reshape(ls_.shape))
+                    extra = torch.autograd.grad(outs, leaves, grad_outputs=gs, allow_unused=True)
+                parts = [nf.detach().reshape(1)]
+                for i, (a, b) in enumerate(offs):
+                    if i == big:
+                        continue
+                    g_ = grads[i]
+                    if extra is not None and extra[i] is not None:
+                        g_ = extra[i] if g_ is None else g_ + extra[i]
+                    parts.append(torch.zeros(b - a, dtype=torch.float64, device=dev) if g_ is None else g_.reshape(-1))
+                st["small"] = torch.cat(parts)
+                g3.capture_end()
+                active[0] = None
+                if ctx is not None:
+                    ctx.all_reduce(st["small"])
+        except BaseException:
+            if active[0] is not None:           # do not leave the stream in capture mode behind an error
+                try:
+                    with torch.cuda.stream(cap):
+                        active[0].capture_end()
+                except Exception:
+                    pass
+            raise
+        finally:
+            ops.defer_reverse(prev)
+            params[big]._before_use = None
+            self.clear_tensors()
+            if gc_was_on:
+                gc.enable()
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
+        st["g1"], st["g2"], st["g3"] = g1, g2, g3
+        st["infos"] = list(self._pending_infos)
+        st["keep"] = [d._tensor for nd in self._all_parameterized() for d in nd.data_holders] + \
+                     [p._fixed_dev for p in self.all_params() if p.fixed]
+        return st
 
     def compute_log_likelihood(self, **kw):
         x = torch.as_tensor(self.get_free_state()).to(default_device())

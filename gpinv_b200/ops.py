@@ -191,6 +191,9 @@ potrf.register_autograd(_potrf_backward, setup_context=_potrf_setup)
 # pass whose result is dropped without a reverse pass never joins the side stream); an entry is dropped
 # only after a host-side wait for the side stream.
 _W_KEEP = []
+# True from the launch of a side-stream inversion until a Python-level ``trtri_side_join`` (a capture that is
+# about to end must join the side stream it forked, and must not wait on an inversion of an earlier capture)
+SIDE_PENDING = [False]
 
 
 @torch.library.custom_op("gpinv::chol_core", mutates_args=(), device_types="cuda")
@@ -222,6 +225,7 @@ def chol_core(X: Tensor, ls: Tensor, mode: int, jitter: float, with_inverse: boo
             del _W_KEEP[0]
         _capi.check(lib.gpinv_trtri_side_f64(_p(Lm), n, _p(W), C.c_void_p(W.data_ptr() + 8 * n * n), n, _st()),
                     "trtri_side")
+        SIDE_PENDING[0] = True
         if not capturing:       # (inside a capture the tensor lives until the captured reverse pass)
             _W_KEEP.append(W)
     else:
@@ -230,10 +234,11 @@ def chol_core(X: Tensor, ls: Tensor, mode: int, jitter: float, with_inverse: boo
 
 
 @torch.library.custom_op("gpinv::chol_core_bwd", mutates_args=(), device_types="cuda")
-def chol_core_bwd(X: Tensor, ls: Tensor, mode: int, L: Tensor, Lbar: Tensor, W: Tensor) -> Tensor:
+def chol_core_bwd(X: Tensor, ls: Tensor, mode: int, L: Tensor, Lbar: Tensor, W: Tensor, w_ready: bool = False) -> Tensor:
     """dObj/d(lengthscales) from dObj/dL: Cholesky reverse (inverse formula, W = L^-1 from the forward
     pass when available) kept as a lower triangle and reduced straight into the lengthscale gradient
-    (no symmetric n x n gradient is formed)."""
+    (no symmetric n x n gradient is formed).  ``w_ready``: the caller has already ordered the stream after the
+    side-stream inversion (``trtri_side_join``)."""
     X = _chk(X, "X")
     ls = _chk(ls, "ls").reshape(-1)
     L = _chk(L, "L")
@@ -245,7 +250,7 @@ def chol_core_bwd(X: Tensor, ls: Tensor, mode: int, L: Tensor, Lbar: Tensor, W: 
     lib = _capi.lib()
     ws = _ws(lib.gpinv_chol_core_bwd_ws_bytes(n, D), X)
     rc = lib.gpinv_chol_core_bwd2_f64(_p(X), n, D, D, _p(ls), ard, mode, _p(L), n, _p(Lbar), n,
-                                      _p(W) if W.numel() else None, _p(out), _p(ws), _st())
+                                      _p(W) if W.numel() else None, 1 if w_ready else 0, _p(out), _p(ws), _st())
     _capi.check(rc, "chol_core_bwd")
     return out
 
@@ -284,13 +289,17 @@ def _chol_core_backward(ctx, Lbar, _info_bar, _w_bar):
     if d is not None and W.numel() and d.accepts(L.shape[0]):
         d.items.append((X, ls, ctx.mode, L, W, Lbar.contiguous()))
         return None, None, None, None, None
-    g = chol_core_bwd(X, ls, ctx.mode, L, Lbar.contiguous(), W)
+    # (the C call joins the side stream unless a Python-level join has already been made -- e.g. at the end of
+    # the CUDA graph that holds the forward pass, whose events a later graph cannot wait on)
+    g = chol_core_bwd(X, ls, ctx.mode, L, Lbar.contiguous(), W, not SIDE_PENDING[0])
+    SIDE_PENDING[0] = False
     return None, g.reshape(ctx.ls_shape), None, None, None
 
 
 def trtri_side_join():
     """Order the current stream after the side-stream inversion started by ``chol_core(with_inverse=True)``."""
     _capi.check(_capi.lib().gpinv_trtri_side_join(_st()), "trtri_side_join")
+    SIDE_PENDING[0] = False
 
 
 def lbar_pack(Lbar: Tensor, G: int) -> Tensor:

@@ -93,10 +93,12 @@ int gpinv_chol_core_bwd_f64(const double* X, int n, int D, int ldx, const double
                             double* ls_bar, void* ws, void* stream);
 /* Same reverse with the explicit inverse W = L^-1 [n,n] supplied (built ahead of time by
  * gpinv_trtri_side_f64 on the library's side stream, overlapping the sampling / likelihood stages:
- * the inverse depends on L only).  The call first makes `stream` wait for that side-stream work. */
+ * the inverse depends on L only).  winv_ready = 0: the call first makes `stream` wait for that side-stream
+ * work; 1: the caller has already done so with gpinv_trtri_side_join (needed when the forward and the reverse
+ * pass are captured into different CUDA graphs: an event of one capture cannot be waited on in another). */
 int gpinv_chol_core_bwd2_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
                              int mode, const double* L, int ldl, const double* Lbar, int ldlb,
-                             const double* Winv, double* ls_bar, void* ws, void* stream);
+                             const double* Winv, int winv_ready, double* ls_bar, void* ws, void* stream);
 /* Winv <- L^-1 on the side stream once the work already enqueued on `stream` is done; `scratch` [n,n].
  * gpinv_trtri_side_join makes `stream` wait for the most recent such inversion. */
 int gpinv_trtri_side_f64(const double* L, int ldl, double* Winv, double* scratch, int n, void* stream);

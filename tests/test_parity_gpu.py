@@ -755,6 +755,33 @@ def test_overlapped_host_path_matches_plain_host_path(n):
         assert np.all(gq[np.triu_indices(n, 1)] == 0.0)
 
 
+@pytest.mark.parametrize("defer_min", [1 << 30, 512])
+def test_graph_replayed_host_pipeline_matches_plain_host_path(defer_min):
+    """enable_cuda_graph + a large state: the host API replays three CUDA graphs cut where the q_sqrt upload
+    and the gradient download slot in (with ``defer_min`` = 512 the Cholesky reverse is in the third graph,
+    behind the cut made by ops.DeferredReverse).  The state and the draws change from call to call."""
+    n = 640
+    m = make_abel_stvgp(n, 300, 16)
+    m.kern.lengthscales = 0.3
+    rng = np.random.RandomState(3)
+    xs = [perturbed_state(m, 0.02, seed=s) for s in range(1, 8)]
+    epss = [rng.randn(1, 16, n) for _ in xs]
+    plain = [tuple(np.array(v) for v in m._objective(x, eps=e)) for x, e in zip(xs, epss)]
+    m.OVERLAP_MIN = 1000
+    m.DEFER_MIN_N = defer_min
+    m.enable_cuda_graph()
+    for k, (x, e, (f0, g0)) in enumerate(zip(xs, epss, plain)):
+        f1, g1 = m._objective(x, eps=e)           # calls 0, 1: eager pipelined path; 2: capture; 3..: replay
+        g1 = np.array(g1)
+        # hyper_tol: the lengthscale gradient is a cancelling sum whose value differs by ~3e-6 ABSOLUTE between
+        # two identical runs of any path (atomics order upstream, amplified by cond(K); tests/gpu_pipeline_spread.py:
+        # same spread through the plain path and both pipeline variants); at these states it is as small as 40
+        assert same_evaluation(f1, g1, float(f0), g0, 4, hyper_tol=1e-6), k
+        gq = g1[-n * n:].reshape(n, n)
+        assert np.all(gq[np.triu_indices(n, 1)] == 0.0)
+    assert any(isinstance(k, tuple) and k and k[0] == "host" for k in m._graphs), list(m._graphs)
+
+
 _DIST_WORKER = r"""
 import os, sys
 sys.path.insert(0, sys.argv[1])
@@ -795,6 +822,15 @@ for overlap_min in (1 << 30, 1000):                               # plain host p
         if not good:
             print("rank %d overlap_min %d: f %r vs %r, grad rel err %.3e" % (rank, overlap_min, f1, f0, rel_err(g1, g0)), flush=True)
         ok = ok and good
+m.enable_cuda_graph(True)                                         # host API replaying its three graphs
+m.OVERLAP_MIN = 1000
+for k in range(5):
+    f1, g1 = m._objective(x, eps=eps)
+    good = close(f1, g1)
+    if not good:
+        print("rank %d graph host pipeline call %d: f %r vs %r, grad rel err %.3e" % (rank, k, f1, f0, rel_err(g1, g0)), flush=True)
+    ok = ok and good
+ok = ok and any(isinstance(k, tuple) and k and k[0] == "host" for k in m._graphs)
 for graph in (False, True):                                       # eager, then graph replay + eager all-reduce
     m.enable_cuda_graph(graph)
     for _ in range(2):
