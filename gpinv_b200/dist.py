@@ -77,6 +77,80 @@ class DistContext(object):
         return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
 
+class SharedHostBuffers(object):
+    """Page-locked host buffers shared by the ranks of ONE node (POSIX shared memory mapped and
+    cudaHostRegister-ed by every rank).  The host API of the sample-sharded evaluation returns the same
+    [value, gradient] on every rank: instead of G device-to-host copies of the whole gradient through the
+    node's memory system, rank g downloads 1/G of it into the shared buffer and a barrier publishes it.
+    All methods are collective."""
+
+    def __init__(self, ctx, count, nbuf=2):
+        self.ctx, self.count = ctx, int(count)
+        self.bufs = []                       # [tensor, mmap, weakref to the array handed out]
+        for _ in range(nbuf):
+            self._add()
+
+    def _add(self):
+        import mmap
+        import os
+        ctx = self.ctx
+        dev = torch.device("cuda", torch.cuda.current_device())
+        tok = torch.randint(0, 2 ** 62, (1,), device=dev, dtype=torch.int64)
+        dist.broadcast(tok, src=0 if ctx.group is None else dist.get_global_rank(ctx.group, 0), group=ctx.group)
+        path = "/dev/shm/gpinv_b200_%x" % int(tok.item())
+        nbytes = 8 * self.count
+        ok = 1
+        fd = -1
+        try:
+            if ctx.rank == 0:
+                fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                os.ftruncate(fd, nbytes)     # zero-filled
+        except OSError:
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=ctx.group)          # (also: the file exists from here on)
+        if int(flag.item()) == 0:
+            raise RuntimeError("cannot create the shared result buffer %s" % path)
+        try:
+            if ctx.rank != 0:
+                fd = os.open(path, os.O_RDWR)
+            mm = mmap.mmap(fd, nbytes)
+            os.close(fd)
+            t = torch.frombuffer(mm, dtype=torch.float64, count=self.count)
+            rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)
+            ok = 1 if int(rc) == 0 else 0
+        except (OSError, ValueError, RuntimeError):
+            ok, mm, t = 0, None, None
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=ctx.group)          # everyone has mapped it
+        if ctx.rank == 0:
+            os.unlink(path)                  # the mappings keep it alive; nothing is left behind on exit
+        if int(flag.item()) == 0:
+            raise RuntimeError("cannot map / page-lock the shared result buffer on every rank (ranks on different "
+                               "nodes?)")
+        self.bufs.append([t, mm, None])
+
+    def acquire(self):
+        """Index of a buffer that no rank's caller still holds an array of (a new one if there is none)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        busy = torch.tensor([1 if (b[2] is not None and b[2]() is not None) else 0 for b in self.bufs], device=dev)
+        dist.all_reduce(busy, op=dist.ReduceOp.MAX, group=self.ctx.group)
+        busy = busy.tolist()
+        for i, b in enumerate(busy):
+            if not b:
+                return i
+        self._add()
+        return len(self.bufs) - 1
+
+    def publish(self):
+        """Barrier: every rank's part of the current buffer has landed (call after synchronising the streams
+        that carried this rank's copies)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t, group=self.ctx.group)
+        t.item()
+
+
 def attach(model, ctx=None):
     """Make ``model._objective`` evaluate its shard and all-reduce [-f, -grad]."""
     if not hasattr(model, "_eps_tensor"):

@@ -745,6 +745,11 @@ class Model(Parameterized):
         cs = st["cs"]
         xt = torch.from_numpy(x)
         h2d = d2h = 0
+        shared = st.get("shared")
+        if shared is not None:
+            # one result buffer for the node: this rank downloads its share of it (see dist.SharedHostBuffers)
+            sb = shared.bufs[shared.acquire()]
+            hout = sb[0]
         for a, b, d in ((0, b0, 0), (b1, n, b0)):           # small blocks: on the compute stream
             if b > a:
                 hin[a:b].copy_(xt[a:b])
@@ -790,36 +795,47 @@ class Model(Parameterized):
             if work is not None:
                 work.wait()
                 ops.tri_expand_(st["qc"], gb)
-            tri_only = getattr(hout, "_gpinv_fresh_zero", False) or getattr(hout, "_gpinv_upper_zero", None) == (b0, nq)
+            tri_only = shared is not None or getattr(hout, "_gpinv_fresh_zero", False) or \
+                getattr(hout, "_gpinv_upper_zero", None) == (b0, nq)
             if tri_only:
-                for r0, r1, _ in st["blocks"]:
+                for k_, (r0, r1, _) in enumerate(st["blocks"]):
+                    if shared is not None and not st["take_np"][k_]:
+                        continue             # another rank's share of the shared buffer
                     off = 8 * (r0 * nq)
                     _capi.check(_capi.lib().gpinv_memcpy2d_async(
                         hout.data_ptr() + 8 * (1 + b0) + off, 8 * nq, gb.data_ptr() + off, 8 * nq,
                         8 * r1, r1 - r0, 2, cs.cuda_stream), "memcpy2d")
                     d2h += 8 * r1 * (r1 - r0)
-                hout._gpinv_upper_zero = (b0, nq)
+                if shared is None:
+                    hout._gpinv_upper_zero = (b0, nq)
             else:
                 hout._gpinv_upper_zero = None
                 hout[1 + b0:1 + b1].copy_(gb.reshape(-1), non_blocking=True)
                 d2h += 8 * (b1 - b0)
-            hout._gpinv_fresh_zero = False
+            if shared is None:
+                hout._gpinv_fresh_zero = False
         st["g3"].replay()
         small = st["small"]
         if ctx is not None:
             ctx.all_reduce(small)
-        hout[:1].copy_(small[:1], non_blocking=True)
-        o = 1
-        for i, (a, b) in enumerate(offs):
-            if i != big:
-                hout[1 + a:1 + b].copy_(small[o:o + b - a], non_blocking=True)
-                o += b - a
-        d2h += 8 * small.numel()
+        if shared is None or ctx.rank == 0:
+            hout[:1].copy_(small[:1], non_blocking=True)
+            o = 1
+            for i, (a, b) in enumerate(offs):
+                if i != big:
+                    hout[1 + a:1 + b].copy_(small[o:o + b - a], non_blocking=True)
+                    o += b - a
+            d2h += 8 * small.numel()
         cur.synchronize()
         cs.synchronize()
         self._pending_infos = list(st["infos"])
         self._check_infos()
         self._last_h2d_bytes, self._last_d2h_bytes = h2d, d2h
+        if shared is not None:
+            shared.publish()
+            base = hout.numpy()
+            sb[2] = weakref.ref(base)
+            return float(base[0]), base[1:]
         return finish()
 
     def _host_pipeline_capture(self, n, params, offs, big, nq, dyn, dev):
@@ -945,6 +961,9 @@ class Model(Parameterized):
         torch.cuda.current_stream().wait_stream(cap)
         torch.cuda.synchronize()
         st["g1"], st["g2"], st["g3"] = g1, g2, g3
+        if ctx is not None and os.environ.get("GPINV_SHARED_RESULT", "1") != "0":
+            from .dist import SharedHostBuffers
+            st["shared"] = SharedHostBuffers(ctx, n + 1)
         st["infos"] = list(self._pending_infos)
         st["keep"] = [d._tensor for nd in self._all_parameterized() for d in nd.data_holders] + \
                      [p._fixed_dev for p in self.all_params() if p.fixed]

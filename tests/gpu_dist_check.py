@@ -1,7 +1,7 @@
 """Multi-GPU parity at the headline size (cfg5), launched under torchrun on N GPUs of one box:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port 29511 tests/gpu_dist_check.py [cfg5|cfg2|mid]
+        --master-port 29511 tests/gpu_dist_check.py [cfg5|cfg2|mid] [all|host]
 
 Every rank evaluates its share of the Monte-Carlo samples; the result (eager, CUDA-graph replay and the
 host API) is compared on rank 0 with the committed compact oracle fixture of the configuration
@@ -21,6 +21,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "cfg5"
+    what = sys.argv[2] if len(sys.argv) > 2 else "all"          # "host": only the graph-replayed host API
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -66,7 +67,7 @@ def main():
             if rank == 0:
                 print("%-28s FAIL %s" % (label, str(e)[:300]), flush=True)
 
-    for graph in (False, True):
+    for graph in ((False, True) if what == "all" else ()):
         m.enable_cuda_graph(graph, static_inputs=graph)
         for rep in range(2):
             f, g = m._objective_device(x, eps=eps)
@@ -85,17 +86,20 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         if rank == 0:
             print("device graph=%s: %.3f ms per evaluation (%.1f evals/s)" % (graph, tt.item(), 1e3 / tt.item()), flush=True)
-    m.enable_cuda_graph(False)
-    for rep in range(2):
-        fh, gh = m._objective(c["x"], eps=c["eps"])
-        check("host API rep %d" % rep, fh, gh)
-    dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(5):
-        m._objective(c["x"], eps=c["eps"])
-    dist.barrier()
-    if rank == 0:
-        print("host API: %.3f ms per evaluation" % (1e3 * (time.perf_counter() - t0) / 5), flush=True)
+    eps_dev = torch.as_tensor(c["eps"]).to(dev)
+    for graph in ((False, True) if what == "all" else (True,)):
+        # graph=True: calls 0 and 1 take the eager pipelined path, call 2 captures, calls 3.. replay
+        m.enable_cuda_graph(graph)
+        for rep in range(5 if graph else 2):
+            fh, gh = m._objective(c["x"], eps=eps_dev)
+            check("host API graph=%s rep %d" % (graph, rep), fh, gh)
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            m._objective(c["x"], eps=eps_dev)
+        dist.barrier()
+        if rank == 0:
+            print("host API graph=%s: %.3f ms per evaluation" % (graph, 1e3 * (time.perf_counter() - t0) / 5), flush=True)
     bad = torch.tensor([len(fails)], device=dev)
     dist.all_reduce(bad)
     dist.destroy_process_group()
