@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <algorithm>
 #include <vector>
 
 namespace gpinv {
@@ -216,6 +217,24 @@ const SchedEntry* get_sched(const GemmParams& p, bool lower, bool small, bool at
   e->split = false;
   for (int c = 1; c < G; ++c)
     if (s.start[c] & 0xffffu) e->split = true;
+  // L2-friendly list order for uniform products (see TmaSched): sort the list positions by (index among the
+  // whole tiles of the owning CTA, CTA) and hand them the tiles of the grid in enumeration order
+  s.use_perm = 0;
+  static const bool no_perm = (getenv("GPINV_TMA_NO_PERM") != nullptr);
+  if (!no_perm && p.kmode == 0 && !lower && p.batch == 1 && T <= TMA_MAX_PERM && T > G && G > 1) {
+    std::vector<std::pair<long long, int>> key((size_t)T);
+    int c = 0;
+    for (int i = 0; i < (int)T; ++i) {
+      while (c + 1 < G && (int)(s.start[c + 1] >> 16) <= i && !((int)(s.start[c + 1] >> 16) == i && (s.start[c + 1] & 0xffffu)))
+        ++c;                                     // owner: the CTA that processes the START of tile i
+      // (a range that starts inside a tile processes that piece last: its first whole tile is the next one)
+      const int off = i - ((int)(s.start[c] >> 16) + ((s.start[c] & 0xffffu) ? 1 : 0));
+      key[(size_t)i] = std::make_pair((long long)off * G + c, i);
+    }
+    std::sort(key.begin(), key.end());
+    for (int j = 0; j < (int)T; ++j) s.perm[key[(size_t)j].second] = (unsigned short)j;
+    s.use_perm = 1;
+  }
   g_sched_cache.push_back(e);
   return e;
 }

@@ -37,10 +37,20 @@ constexpr int TMA_MAX_CTAS = 448;
 
 // Work partition of one launch: CTA c owns the units [start[c], start[c+1]) of the ordered tile
 // list; a unit position is (global tile index << 16) | k-tile offset inside the tile.
+// `perm` (use_perm != 0; uniform, non-triangular, un-batched products with <= TMA_MAX_PERM tiles): list
+// position -> tile index of the problem.  The list is ordered so that the positions the CTAs work on AT THE
+// SAME TIME (same offset from the start of their ranges) are neighbours in the tile grid -- one wave of 148
+// CTAs then covers all row panels of ~18 column panels, every operand panel is fetched from DRAM once and
+// shared through L2.  With the plain order (CTA c owns tiles 3.46 c ...) each CTA walked the row panels of
+// "its" column panel one after the other and the column panels were re-read from DRAM for every row panel:
+// 2.49 GB per Abel-transform launch against 0.37 GB algorithmic (ncu, profiles/r2_abel_gemm_ncu_full.txt).
+constexpr int TMA_MAX_PERM = 1024;
 struct TmaSched {
   int nctas;
   int total_tiles;
+  int use_perm;
   unsigned start[TMA_MAX_CTAS + 1];
+  unsigned short perm[TMA_MAX_PERM];
 };
 
 template <int TM_, int TN_, int WM_, int WN_, int STAGES_, int MINB_, int REG_CONS_, int REG_PROD_>
@@ -123,10 +133,11 @@ struct TmaWork {
 };
 
 template <class Cfg, unsigned EF>
-__device__ __forceinline__ void tma_decode(const GemmParams& p, int gtile, TmaWork& w) {
+__device__ __forceinline__ void tma_decode(const GemmParams& p, const TmaSched& sched, int gtile, TmaWork& w) {
   w.gtile = gtile;
   w.z = gtile / p.ntiles;
   w.tile_x = gtile - w.z * p.ntiles;
+  if (sched.use_perm) w.tile_x = sched.perm[gtile];      // (un-batched: gtile == list position)
   int tm, tn;
   gemm_decode_tile(w.tile_x, p.tiles_m, p.tiles_n, p.kmode, (EF & EF_LOWER) != 0, tm, tn);
   w.m0 = tm * Cfg::BM;
@@ -306,6 +317,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int t_end = (int)(u_end >> 16), k_end = (int)(u_end & 0xffffu);
   // tiles touched: t_begin .. t_end (t_end only when k_end > 0)
   const int t_stop = (k_end > 0) ? t_end + 1 : t_end;
+  // Processing order (uniform products, use_perm): a range that starts in the middle of a tile takes that
+  // partial piece LAST.  All CTAs then start their whole tiles together and sweep k in lock-step, so the
+  // CTAs that share an operand panel ask L2 for the same k-slice at the same time; the partial pieces, whose
+  // k offsets are staggered by construction, come at the end.
+  const int t_cnt = t_stop - t_begin;
+  const bool rotate = sched.use_perm && k_begin > 0 && t_cnt > 1;
 
   if (warp >= NCONS / 32) {
     // =============================== TMA producer ===============================
@@ -313,9 +330,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (warp == NCONS / 32 && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int gt = t_begin; gt < t_stop; ++gt) {
+      for (int ti = 0; ti < t_cnt; ++ti) {
+        const int gt = rotate ? ((ti + 1 < t_cnt) ? t_begin + 1 + ti : t_begin) : t_begin + ti;
         TmaWork w;
-        tma_decode<Cfg, EF>(p, gt, w);
+        tma_decode<Cfg, EF>(p, sched, gt, w);
         const int kf = (gt == t_begin) ? k_begin : 0;
         const int kl = (gt == t_end) ? k_end : w.ktiles;
         const int zA = p.strideA ? w.z : 0, zB = p.strideB ? w.z : 0;
@@ -369,9 +387,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   int stage = 0;
   uint32_t phase = 0;
-  for (int gt = t_begin; gt < t_stop; ++gt) {
+  for (int ti = 0; ti < t_cnt; ++ti) {
+    const int gt = rotate ? ((ti + 1 < t_cnt) ? t_begin + 1 + ti : t_begin) : t_begin + ti;
     TmaWork w;
-    tma_decode<Cfg, EF>(p, gt, w);
+    tma_decode<Cfg, EF>(p, sched, gt, w);
     w.k_first = (gt == t_begin) ? k_begin : 0;
     w.k_last = (gt == t_end) ? k_end : w.ktiles;
 

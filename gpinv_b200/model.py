@@ -877,6 +877,12 @@ class Model(Parameterized):
             g1.capture_end()
             g2.capture_begin(pool=g1.pool(), **mode)
             active[0] = g2
+            if later is not None:
+                # sample sharding: the upload is short, so L^-1 is built beside the sampling stage (second graph)
+                # instead of in front of the upload wait (first graph)
+                for L_, W_ in later:
+                    ops.start_inverse(L_, W_)
+                del later[:]
 
         active = [None]
         torch.cuda.synchronize()
@@ -885,6 +891,8 @@ class Model(Parameterized):
         gc_was_on = gc.isenabled()
         gc.disable()
         prev = ops.defer_reverse(col)
+        later = [] if ctx is not None else None
+        ops.INVERSE_LATER = later
         try:
             with torch.cuda.stream(cap):
                 g1.capture_begin(**mode)
@@ -909,6 +917,8 @@ class Model(Parameterized):
                     st["rs_in"] = [ops.lbar_pack(it[5], G) for it in col.items]
                     st["rs_out"] = [torch.empty(r.numel() // G, dtype=torch.float64, device=dev) for r in st["rs_in"]]
                     st["qc"] = ops.tri_compact(gb)
+                if ops.SIDE_PENDING[0]:
+                    ops.trtri_side_join()
                 g2.capture_end()
                 active[0] = None
                 if ctx is not None:             # the ranks' NCCL call order stays aligned with the replay's
@@ -954,6 +964,7 @@ class Model(Parameterized):
             raise
         finally:
             ops.defer_reverse(prev)
+            ops.INVERSE_LATER = None
             params[big]._before_use = None
             self.clear_tensors()
             if gc_was_on:

@@ -223,9 +223,10 @@ def chol_core(X: Tensor, ls: Tensor, mode: int, jitter: float, with_inverse: boo
         if not capturing and len(_W_KEEP) >= 4:
             _capi.check(lib.gpinv_trtri_side_sync(), "trtri_side_sync")      # idle unless a result was dropped
             del _W_KEEP[0]
-        _capi.check(lib.gpinv_trtri_side_f64(_p(Lm), n, _p(W), C.c_void_p(W.data_ptr() + 8 * n * n), n, _st()),
-                    "trtri_side")
-        SIDE_PENDING[0] = True
+        if INVERSE_LATER is not None:
+            INVERSE_LATER.append((Lm, W))        # the caller starts the inversion itself (start_inverse)
+        else:
+            start_inverse(Lm, W)
         if not capturing:       # (inside a capture the tensor lives until the captured reverse pass)
             _W_KEEP.append(W)
     else:
@@ -294,6 +295,20 @@ def _chol_core_backward(ctx, Lbar, _info_bar, _w_bar):
     g = chol_core_bwd(X, ls, ctx.mode, L, Lbar.contiguous(), W, not SIDE_PENDING[0])
     SIDE_PENDING[0] = False
     return None, g.reshape(ctx.ls_shape), None, None, None
+
+
+# None, or a list: chol_core(with_inverse=True) then only allocates W and records (L, W) here; the caller
+# launches the inversion later with start_inverse (the graph-replayed host pipeline starts it in the graph
+# that holds the sampling stage, so that it runs beside that stage instead of in front of the upload wait)
+INVERSE_LATER = None
+
+
+def start_inverse(Lm: Tensor, W: Tensor):
+    """W[0] <- L^-1 on the library's side stream, behind the work already enqueued on the current stream."""
+    n = Lm.shape[0]
+    _capi.check(_capi.lib().gpinv_trtri_side_f64(_p(Lm), n, _p(W), C.c_void_p(W.data_ptr() + 8 * n * n), n, _st()),
+                "trtri_side")
+    SIDE_PENDING[0] = True
 
 
 def trtri_side_join():
