@@ -173,10 +173,13 @@ def potrf_bwd(L: Tensor, Lbar: Tensor) -> Tensor:
 
 def _potrf_setup(ctx, inputs, output):
     ctx.save_for_backward(output[0])
+    ctx.set_materialize_grads(False)      # no zero tensors for the gradients of outputs nobody differentiates
 
 
 def _potrf_backward(ctx, Lbar, _info_bar):
     (L,) = ctx.saved_tensors
+    if Lbar is None:
+        return None
     return potrf_bwd(L, Lbar.contiguous())
 
 
@@ -261,6 +264,8 @@ def _chol_core_setup(ctx, inputs, output):
     ctx.save_for_backward(X, ls, output[0], output[2])
     ctx.mode = mode
     ctx.ls_shape = ls.shape
+    # (materialised, the never-used gradient of W alone was a 268 MB zero fill per evaluation at n = 4096)
+    ctx.set_materialize_grads(False)
 
 
 class DeferredReverse(object):
@@ -286,6 +291,8 @@ def defer_reverse(collector):
 
 def _chol_core_backward(ctx, Lbar, _info_bar, _w_bar):
     X, ls, L, W = ctx.saved_tensors
+    if Lbar is None:
+        return None, None, None, None, None
     d = _DEFER
     if d is not None and W.numel() and d.accepts(L.shape[0]):
         d.items.append((X, ls, ctx.mode, L, W, Lbar.contiguous()))
@@ -471,6 +478,7 @@ def _sample_setup(ctx, inputs, output):
     ctx.save_for_backward(Lc, sqrt_v, Q, E, U, expF)
     ctx.q_diag = q_diag
     ctx.want_exp = want_exp
+    ctx.set_materialize_grads(False)
 
 
 def _sample_backward(ctx, Fbar, expFbar, klbar, Ubar_unused):
@@ -565,6 +573,7 @@ def _kron_setup(ctx, inputs, output):
     ctx.save_for_backward(L1, L2, sqrt_v, Q, E, U, T, expF)
     ctx.q_diag = q_diag
     ctx.want_exp = want_exp
+    ctx.set_materialize_grads(False)
 
 
 def _kron_backward(ctx, Fbar, expFbar, klbar, Ubar_unused, Tbar_unused):
@@ -654,10 +663,13 @@ def abel_bwd(Rs: Tensor, A: Tensor, expF: Tensor, coef: Tensor) -> Tensor:
 def _abel_setup(ctx, inputs, output):
     F, expF, A, Y = inputs
     ctx.save_for_backward(output[1], A, expF)
+    ctx.set_materialize_grads(False)      # (the unused gradient of Rs [S,M] was a 67 MB zero fill)
 
 
 def _abel_backward(ctx, g_ss, g_rs_unused):
     Rs, A, expF = ctx.saved_tensors
+    if g_ss is None:
+        return None, None, None, None
     # d sumsq / dF[s,j] = 2 sum_m Rs[s,m] * (-A[m,j] expF[s,j])
     Fbar = abel_bwd(Rs, A, expF, (-2.0 * g_ss).reshape(1).contiguous())
     return Fbar, None, None, None
@@ -718,10 +730,13 @@ def spec_bwd(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, Y: Tensor, P: Tens
 def _spec_setup(ctx, inputs, output):
     F, A, cosT, lam, Y = inputs
     ctx.save_for_backward(F, A, cosT, lam, Y, output[1])
+    ctx.set_materialize_grads(False)
 
 
 def _spec_backward(ctx, g_ss, g_p_unused):
     F, A, cosT, lam, Y, P = ctx.saved_tensors
+    if g_ss is None:
+        return None, None, None, None, None
     return spec_bwd(F, A, cosT, lam, Y, P, (2.0 * g_ss).reshape(1).contiguous()), None, None, None, None
 
 
@@ -770,6 +785,7 @@ def _unpack_setup(ctx, inputs, output):
     x, offsets, transforms = inputs
     ctx.save_for_backward(x)
     ctx.offsets, ctx.transforms = list(offsets), list(transforms)
+    ctx.set_materialize_grads(False)      # blocks without a gradient arrive as None: pack_grad writes their zeros
 
 
 def _unpack_backward(ctx, grads):
