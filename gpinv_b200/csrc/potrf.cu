@@ -370,8 +370,16 @@ __global__ void finalize_sym_kernel(double* __restrict__ Ab, int n, int ld) {
 // ---------------------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------------------
+// The opt-in to > 48 KB of dynamic shared memory is a per-DEVICE attribute of a kernel: one flag per device.
+static bool* device_flag(bool (&flags)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return &flags[dev];
+}
+
 static int set_smem_attrs() {
-  static bool done = false;
+  static bool done_dev[64] = {};
+  bool& done = *device_flag(done_dev);
   if (done) return GPINV_OK;
   cudaError_t e;
   e = cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pcfg::PANEL_SMEM);
@@ -746,7 +754,8 @@ __global__ void mirror_lower_kernel(double* __restrict__ A, int n, int ld) {
 static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cudaStream_t st,
                      int stop = 0x7fffffff, int ws_slot = 0) {
   using namespace pcfg;
-  static bool attr = false;
+  static bool attr_dev[64] = {};
+  bool& attr = *device_flag(attr_dev);
   const int smem = (NB * LDT + NB + NB * LDR) * 8;
   if (!attr) {
     GPINV_TRY(cudaFuncSetAttribute(trtri_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1175,7 +1184,8 @@ __global__ void __launch_bounds__(pcfg::TRSM_ROWS) trsm_rlt_kernel(const double*
 
 int trsm_rlt_f64(const double* L, int ldl, double* X, int ldx, int m, int n, cudaStream_t st) {
   using namespace pcfg;
-  static bool attr = false;
+  static bool attr_dev[64] = {};
+  bool& attr = *device_flag(attr_dev);
   if (!attr) {
     GPINV_TRY(cudaFuncSetAttribute(trsm_rlt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              TRSM_SMEM));
