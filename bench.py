@@ -208,7 +208,7 @@ def insitu_abel_seconds(m, x, eps):
     was_graph = m._use_graph
     m._use_graph = False
     try:
-        for _ in range(3):
+        for _ in range(7):
             m._objective_device(x, eps=eps)
         torch.cuda.synchronize()
         ts = [a.elapsed_time(b) / 1e3 for a, b in ops.TIMERS.get("abel_resid", [])]
