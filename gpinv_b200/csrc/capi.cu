@@ -33,7 +33,8 @@ int potrf_bwd_hybrid_ex_f64(const double*, int, double*, int, int, double*, int,
 int trtri_side_f64(const double*, int, double*, double*, int, cudaStream_t);
 int trtri_side_join_f64(cudaStream_t);
 int trtri_side_sync_f64();
-int potrf_ex_f64(double*, int, int, int*, int, cudaStream_t);
+int potrf_ex_f64(double*, int, int, int*, int, cudaStream_t, double* Winv = nullptr, double* Tinv = nullptr,
+                 int* inv_done_out = nullptr);
 int tril_copy_f64(const double*, int, double*, int, int, cudaStream_t);
 int lbar_pack_f64(const double*, int, int, int, int, double*, cudaStream_t);
 int tri_compact_f64(const double*, int, int, double*, cudaStream_t);
@@ -76,9 +77,9 @@ int kl_white_bwd_f64(const double*, const double*, int, int, int, const double*,
 int adam_step_f64(double*, double*, double*, const double*, long long, double, double, double, double, long long*,
                   cudaStream_t);
 int spec_fwd_f64(const double*, const double*, const double*, const double*, const double*, int, int,
-                 int, int, double*, double*, cudaStream_t);
+                 int, int, double, double*, double*, cudaStream_t);
 int spec_bwd_f64(const double*, const double*, const double*, const double*, const double*,
-                 const double*, const double*, int, int, int, int, double*, cudaStream_t);
+                 const double*, const double*, int, int, int, int, double, double*, cudaStream_t);
 }  // namespace gpinv
 
 using namespace gpinv;
@@ -229,6 +230,19 @@ int gpinv_chol_core_f64(const double* X, int n, int D, int ldx, const double* ls
   return potrf_ex_f64(L, n, ldl, info, 1, ST(stream));
 }
 
+int gpinv_chol_core_inv_f64(const double* X, int n, int D, int ldx, const double* ls, int ard, int mode,
+                            double jitter, double* L, int ldl, int* info, double* Winv, double* scratch, void* ws,
+                            void* stream) {
+  if (n <= 0 || D <= 0 || ldl < n || !Winv || !scratch) return GPINV_ERR_ARG;
+  int rc = kbuild_ex_f64(X, nullptr, n, n, D, ldx, ldx, ls, ard, mode, jitter, L, ldl,
+                         static_cast<double*>(ws), 1, ST(stream));
+  if (rc) return rc;
+  int interleaved = 0;
+  rc = potrf_ex_f64(L, n, ldl, info, 1, ST(stream), Winv, scratch, &interleaved);
+  if (rc || interleaved) return rc;
+  return trtri_side_f64(L, ldl, Winv, scratch, n, ST(stream));     // small n: behind the factorisation
+}
+
 int gpinv_trtri_side_f64(const double* L, int ldl, double* Winv, double* scratch, int n, void* stream) {
   if (n <= 0 || ldl < n || !Winv || !scratch) return GPINV_ERR_ARG;
   return trtri_side_f64(L, ldl, Winv, scratch, n, ST(stream));
@@ -340,14 +354,14 @@ int gpinv_abel_bwd_f64(const double* Rs, const double* A, int lda, const double*
 }
 
 int gpinv_spec_fwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
-                       const double* Y, int n, int m, int k, int S, double* P, double* sumsq,
+                       const double* Y, int n, int m, int k, int S, double dlam, double* P, double* sumsq,
                        void* stream) {
-  return spec_fwd_f64(F, A, cosT, lam, Y, n, m, k, S, P, sumsq, ST(stream));
+  return spec_fwd_f64(F, A, cosT, lam, Y, n, m, k, S, dlam, P, sumsq, ST(stream));
 }
 int gpinv_spec_bwd_f64(const double* F, const double* A, const double* cosT, const double* lam,
                        const double* Y, const double* P, const double* coef, int n, int m, int k,
-                       int S, double* Fbar, void* stream) {
-  return spec_bwd_f64(F, A, cosT, lam, Y, P, coef, n, m, k, S, Fbar, ST(stream));
+                       int S, double dlam, double* Fbar, void* stream) {
+  return spec_bwd_f64(F, A, cosT, lam, Y, P, coef, n, m, k, S, dlam, Fbar, ST(stream));
 }
 
 int gpinv_kron_apply_f64(const double* L1, int n1, const double* L2, int n2, const double* U, int batch,

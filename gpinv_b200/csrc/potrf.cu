@@ -403,11 +403,16 @@ static int pick_splitk(int M, int N, int K, bool lower) {
   return max(s, 1);
 }
 
+static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cudaStream_t st, int stop = 0x7fffffff,
+                     int ws_slot = 0, int ldw = 0);
+
 // Side stream + events for the look-ahead (one set per device, created on first use).
 struct LookAhead {
   cudaStream_t side = nullptr;
+  cudaStream_t inv = nullptr;                  // lowest priority: the inversion interleaved with the factorisation
   cudaEvent_t evP = nullptr, evB = nullptr;
   cudaEvent_t evF = nullptr, evW = nullptr;    // forward factor ready / explicit inverse ready (see trtri_side_f64)
+  cudaEvent_t evI = nullptr;                   // outer panel factored (interleaved inversion)
   bool ok = false;
 };
 static LookAhead* lookahead_for_current_device() {
@@ -417,6 +422,10 @@ static LookAhead* lookahead_for_current_device() {
   LookAhead& la = table[dev];
   if (!la.ok) {
     if (cudaStreamCreateWithFlags(&la.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    int prio_lo = 0, prio_hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&la.inv, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&la.evI, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&la.evP, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&la.evB, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&la.evF, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -438,23 +447,71 @@ __global__ void zero_upper_diag_blocks_kernel(double* __restrict__ A, int n, int
   if (r < n && c < n && c < base + nbo && r < base + nbo && c > r) A[(size_t)r * lda + c] = 0.0;
 }
 
-int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaStream_t st);
+int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaStream_t st, double* Winv = nullptr,
+                 double* Tinv = nullptr, int* inv_done_out = nullptr);
 
 int potrf_f64(double* A, int n, int lda, int* info, cudaStream_t st) {
   return potrf_ex_f64(A, n, lda, info, 0, st);
 }
 
+// GEMM with a CTA cap (runs beside the factorisation's kernel chain), split-K workspace half `ws_slot`
+static int gemm_cap(int la_, int lb_, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
+                    int ldb, double* out, int ldo, int kmode, int cap, int ws_slot, cudaStream_t st) {
+  GemmParams p = {};
+  p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.M = M; p.N = N; p.K = K;
+  p.alpha = alpha; p.beta = 0.0; p.Cin = nullptr; p.ldcin = 0; p.out = out; p.ldo = ldo;
+  p.kmode = kmode; p.splitk = 1; p.allow_split = 1; p.max_ctas = cap; p.ws_slot = ws_slot;
+  return gemm_launch(la_, lb_, EF_BETA, p, st);
+}
+
+// Row block [r0, r1) of W = L^-1 (W, T: n x n, ld n; rows < r0 of W done; strict upper part of W zero):
+//   W_II = L_II^-1;   W[I, :r0] = -W_II (L[I, :r0] W[:r0, :r0]).
+// Needs only L[:r1, :r1], i.e. it can run as soon as the outer panel that ends at column r1 is factored.
+static int trtri_row_block(const double* L, int ldl, double* W, double* T, int n, int r0, int r1, int cap,
+                           cudaStream_t st) {
+  const int bw = r1 - r0;
+  int rc = trtri_f64(L + (size_t)r0 * ldl + r0, ldl, W + (size_t)r0 * n + r0, T + (size_t)r0 * n + r0, bw, st,
+                     0x7fffffff, 1, n);
+  if (rc || r0 == 0) return rc;
+  rc = gemm_cap(LK, LMN, bw, r0, r0, 1.0, L + (size_t)r0 * ldl, ldl, W, n, T + (size_t)r0 * n, n, 2, cap, 1, st);
+  if (rc) return rc;                                        // T = L[I, :r0] W[:r0, :r0]   (W lower: k >= column)
+  return gemm_cap(LK, LMN, bw, r0, bw, -1.0, W + (size_t)r0 * n + r0, n, T + (size_t)r0 * n, n, W + (size_t)r0 * n, n,
+                  3, cap, 1, st);                           // W[I, :r0] = -W_II T         (W_II lower: k <= row)
+}
+
 // upper_is_zero: the caller built only the lower triangle (strict upper part = 0).  The
 // factorisation never reads above the diagonal and only dirties the upper parts of the NBO-wide
 // diagonal blocks, so the final clean-up touches those instead of the whole matrix.
-int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaStream_t st) {
+// Winv / Tinv (optional, n x n each; EXPERIMENT, see below): W = L^-1 built INSIDE the factorisation, row block
+// by row block, on a third, lowest-priority stream.  Row block I needs the leading (I+1) outer panels of L only,
+// its cost grows like I^2 while the trailing update shrinks like (N-I)^2, so the idea was that the inversion
+// fills the SMs the late panels leave idle instead of competing with the sampling stage afterwards.
+// *inv_done_out = 1 when the inversion was enqueued here (the caller joins evW through trtri_side_join_f64).
+int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaStream_t st, double* Winv,
+                 double* Tinv, int* inv_done_out) {
   using namespace pcfg;
   int rc = set_smem_attrs();
   if (rc) return rc;
+  if (inv_done_out) *inv_done_out = 0;
   GPINV_TRY(cudaMemsetAsync(info, 0, 2 * sizeof(int), st));
   static const bool no_la = (getenv("GPINV_NO_LOOKAHEAD") != nullptr);
   LookAhead* la = (n > 2 * NBO && !no_la) ? lookahead_for_current_device() : nullptr;
   bool side_pending = false;
+  // Measured at n = 4096 (tests/gpu_cholinv_time.py, graph replay): factorisation 2.13 ms; factorisation + inversion
+  // behind it (recursive doubling, whole machine) 3.10 ms; interleaved 3.25 ms at best (cap 148, from panel 0; 4.50 ms
+  // with cap 64 from panel 6): the row-block form has 256-row GEMMs with few, long tiles, its heavy row blocks only
+  // become available at the very end, and the diagonal-block inversions are latency chains.  So it is OFF by default
+  // (GPINV_INTERLEAVED_INVERSE=1 to enable).
+  static const bool inter = (getenv("GPINV_INTERLEAVED_INVERSE") != nullptr);
+  static const int inv_cap = getenv("GPINV_INV_CAP") ? atoi(getenv("GPINV_INV_CAP")) : 148;
+  static const int inv_from = getenv("GPINV_INV_FROM") ? atoi(getenv("GPINV_INV_FROM")) : 0;
+  const bool inv_on = la && Winv && Tinv && inter && lda == n;
+  int inv_rows = 0;                    // row blocks [0, inv_rows) of W are enqueued
+  if (inv_on) {
+    GPINV_TRY(cudaEventRecord(la->evF, st));
+    GPINV_TRY(cudaStreamWaitEvent(la->inv, la->evF, 0));
+    GPINV_TRY(cudaMemsetAsync(Winv, 0, (size_t)n * n * sizeof(double), la->inv));
+  }
   for (int o = 0; o < n; o += NBO) {
     const int w = min(NBO, n - o);
     // Inside an outer panel the 64-column sub-panels are brought up to date either right-looking (after
@@ -481,6 +538,18 @@ int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaSt
       }
     }
     const int t0 = o + w;   // first trailing row / column
+    if (inv_on) {
+      const int pi = o / NBO;
+      if (pi >= inv_from || t0 >= n) {
+        GPINV_TRY(cudaEventRecord(la->evI, st));            // outer panels 0 .. pi are final
+        GPINV_TRY(cudaStreamWaitEvent(la->inv, la->evI, 0));
+        for (; inv_rows <= pi; ++inv_rows) {
+          const int r0 = inv_rows * NBO, r1 = min(n, r0 + NBO);
+          rc = trtri_row_block(A, lda, Winv, Tinv, n, r0, r1, inv_cap, la->inv);
+          if (rc) return rc;
+        }
+      }
+    }
     if (t0 >= n) break;
     double* P = A + (size_t)t0 * lda + o;
     if (!la) {
@@ -523,6 +592,10 @@ int potrf_ex_f64(double* A, int n, int lda, int* info, int upper_is_zero, cudaSt
     }
   }
   if (side_pending) GPINV_TRY(cudaStreamWaitEvent(st, la->evB, 0));
+  if (inv_on) {
+    GPINV_TRY(cudaEventRecord(la->evW, la->inv));
+    if (inv_done_out) *inv_done_out = 1;
+  }
   dim3 blk(32, 8);
   if (upper_is_zero) {
     dim3 grd(cdiv(NBO, 32), cdiv(NBO, 8), cdiv(n, NBO));
@@ -751,8 +824,9 @@ __global__ void mirror_lower_kernel(double* __restrict__ A, int n, int ld) {
 // W (n x n, ld = n, zero on entry) <- L^{-1};  T: n x n scratch.
 // With `stop` < n only the diagonal blocks of size `stop` (a power-of-two multiple of NB, blocks
 // aligned at multiples of `stop`) are inverted; the rest of W stays zero.
-static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cudaStream_t st,
-                     int stop = 0x7fffffff, int ws_slot = 0) {
+static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cudaStream_t st, int stop, int ws_slot,
+                     int ldw) {
+  if (ldw <= 0) ldw = n;        // W and T are n x n with leading dimension ldw
   using namespace pcfg;
   static bool attr_dev[64] = {};
   bool& attr = *device_flag(attr_dev);
@@ -762,7 +836,7 @@ static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cuda
                              smem));
     attr = true;
   }
-  trtri_leaf_kernel<<<cdiv(n, NB), NB, smem, st>>>(L, ldl, W, n, n);
+  trtri_leaf_kernel<<<cdiv(n, NB), NB, smem, st>>>(L, ldl, W, ldw, n);
   GPINV_CHECK_LAUNCH();
   int rc;
   for (int s = NB; s < n && s < stop; s *= 2) {
@@ -770,7 +844,7 @@ static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cuda
     int nfull = 0;
     while ((long long)(nfull + 1) * 2 * s <= n) ++nfull;
     const long long strL = (long long)2 * s * ldl + 2 * s;
-    const long long strW = (long long)2 * s * n + 2 * s;
+    const long long strW = (long long)2 * s * ldw + 2 * s;
     for (int pass = 0; pass < 2; ++pass) {
       const int i0 = pass == 0 ? 0 : nfull * 2 * s;
       const int batch = pass == 0 ? nfull : 1;
@@ -779,12 +853,12 @@ static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cuda
       if (batch <= 0 || rows <= 0 || m0 >= n) continue;
       // T21 = L21 W11   (W11 lower: B(c,k) = W11[k][c] is zero for k < c)
       rc = gemm_batched(LK, LMN, rows, s, s, 1.0, L + (size_t)m0 * ldl + i0, ldl, strL,
-                        W + (size_t)i0 * n + i0, n, strW, 0.0, T + (size_t)m0 * n + i0, n, strW,
+                        W + (size_t)i0 * ldw + i0, ldw, strW, 0.0, T + (size_t)m0 * ldw + i0, ldw, strW,
                         batch, false, 2, st, 1, ws_slot);
       if (rc) return rc;
       // W21 = -W22 T21  (W22 lower: A(r,k) zero for k > r)
-      rc = gemm_batched(LK, LMN, rows, s, rows, -1.0, W + (size_t)m0 * n + m0, n, strW,
-                        T + (size_t)m0 * n + i0, n, strW, 0.0, W + (size_t)m0 * n + i0, n, strW,
+      rc = gemm_batched(LK, LMN, rows, s, rows, -1.0, W + (size_t)m0 * ldw + m0, ldw, strW,
+                        T + (size_t)m0 * ldw + i0, ldw, strW, 0.0, W + (size_t)m0 * ldw + i0, ldw, strW,
                         batch, false, 3, st, 1, ws_slot);
       if (rc) return rc;
     }
@@ -1110,6 +1184,7 @@ int trtri_side_sync_f64() {
   LookAhead* la = lookahead_for_current_device();
   if (!la) return GPINV_ERR_CUDA;
   GPINV_TRY(cudaStreamSynchronize(la->side));
+  GPINV_TRY(cudaStreamSynchronize(la->inv));
   return GPINV_OK;
 }
 

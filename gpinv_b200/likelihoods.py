@@ -118,16 +118,33 @@ class SpecAbelLikelihood(Likelihood):
         # so a captured CUDA graph keeps reading valid memory)
         self._AmatT = DataHolder(np.ascontiguousarray(np.asarray(Amat, dtype=np.float64).T))
         self._cosTT = DataHolder(np.ascontiguousarray(np.asarray(cosTheta, dtype=np.float64).T))
+        self._lam_step = self._uniform_step(lam)
+        self.lam._on_change = lambda arr: setattr(self, "_lam_step", self._uniform_step(arr))
         self.Amat._on_change = lambda arr: self._AmatT.set_data(np.ascontiguousarray(arr.T))
         self.cosT._on_change = lambda arr: self._cosTT.set_data(np.ascontiguousarray(arr.T))
 
     def _geometry_T(self):
         return self._AmatT, self._cosTT
 
+    @staticmethod
+    def _uniform_step(lam):
+        """Spacing of the wavelength grid when it is uniform (np.linspace, as in the notebook) -- the kernels then
+        advance the Gaussian line shape along the wavelength index by a recurrence -- else 0.0."""
+        lam = np.asarray(lam, dtype=np.float64).reshape(-1)
+        if lam.size < 3:
+            return 0.0
+        step = (lam[-1] - lam[0]) / (lam.size - 1)
+        if step == 0.0 or np.max(np.abs(np.diff(lam) - step)) > 1e-12 * max(abs(step), 1e-3 * np.max(np.abs(lam))):
+            return 0.0
+        return float(step)
+
+    def _dlam(self):
+        return self._lam_step
+
     def sample_F(self, F):
         """[S,k,m] transformed samples (fused sm_100a kernel)."""
         At, cTt = self._geometry_T()
-        return ops.spec_transform(_internal(F), At, cTt, self.lam.reshape(-1).contiguous())
+        return ops.spec_transform(_internal(F), At, cTt, self.lam.reshape(-1).contiguous(), self._dlam())
 
     def sample_F_torch(self, F):
         """The notebook's tile-and-reduce formulation in torch ops (kept for user subclasses)."""
@@ -144,7 +161,7 @@ class SpecAbelLikelihood(Likelihood):
 
     def logp_sum(self, F, Y, expF=None):
         At, cTt = self._geometry_T()
-        ss, P = ops.spec_resid(_internal(F), At, cTt, self.lam.reshape(-1).contiguous(), Y.contiguous())
+        ss, P = ops.spec_resid(_internal(F), At, cTt, self.lam.reshape(-1).contiguous(), Y.contiguous(), self._dlam())
         var = self.variance
         return -0.5 * float(P.numel()) * (LOG2PI + torch.log(var)) - 0.5 * ss / var
 

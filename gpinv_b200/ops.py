@@ -214,9 +214,6 @@ def chol_core(X: Tensor, ls: Tensor, mode: int, jitter: float, with_inverse: boo
     info = torch.zeros(2, dtype=torch.int32, device=X.device)
     lib = _capi.lib()
     ws = _ws(lib.gpinv_chol_core_ws_bytes(n, D), X)
-    rc = lib.gpinv_chol_core_f64(_p(X), n, D, D, _p(ls), ard, mode, float(jitter), _p(Lm), n, _p(info),
-                                 _p(ws), _st())
-    _capi.check(rc, "chol_core")
     if with_inverse and n > 64:
         # W[0] = L^-1, W[1] = scratch of the inversion: ONE tensor, returned and saved for the reverse pass,
         # so that neither half can be recycled (by the caching allocator, or by a captured graph's pool)
@@ -227,12 +224,22 @@ def chol_core(X: Tensor, ls: Tensor, mode: int, jitter: float, with_inverse: boo
             _capi.check(lib.gpinv_trtri_side_sync(), "trtri_side_sync")      # idle unless a result was dropped
             del _W_KEEP[0]
         if INVERSE_LATER is not None:
+            rc = lib.gpinv_chol_core_f64(_p(X), n, D, D, _p(ls), ard, mode, float(jitter), _p(Lm), n, _p(info),
+                                         _p(ws), _st())
+            _capi.check(rc, "chol_core")
             INVERSE_LATER.append((Lm, W))        # the caller starts the inversion itself (start_inverse)
         else:
-            start_inverse(Lm, W)
+            # factorisation with the inversion interleaved (row blocks of W on a low-priority stream of the library)
+            rc = lib.gpinv_chol_core_inv_f64(_p(X), n, D, D, _p(ls), ard, mode, float(jitter), _p(Lm), n, _p(info),
+                                             _p(W), C.c_void_p(W.data_ptr() + 8 * n * n), _p(ws), _st())
+            _capi.check(rc, "chol_core_inv")
+            SIDE_PENDING[0] = True
         if not capturing:       # (inside a capture the tensor lives until the captured reverse pass)
             _W_KEEP.append(W)
     else:
+        rc = lib.gpinv_chol_core_f64(_p(X), n, D, D, _p(ls), ard, mode, float(jitter), _p(Lm), n, _p(info),
+                                     _p(ws), _st())
+        _capi.check(rc, "chol_core")
         W = torch.empty(0, dtype=torch.float64, device=X.device)
     return Lm, info, W
 
@@ -690,54 +697,59 @@ def sumsq(x: Tensor) -> Tensor:
 # T16 spectroscopic Abel transform
 # --------------------------------------------------------------------------------------
 @torch.library.custom_op("gpinv::spec_transform", mutates_args=(), device_types="cuda")
-def spec_transform(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor) -> Tensor:
+def spec_transform(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, dlam: float = 0.0) -> Tensor:
     """P [S,k,m] from F [3,S,n] (notebooks/Spectroscopic_Abel_inversion.ipynb:316-346).
-    A, cosT: the geometry matrices TRANSPOSED to [n,m] (see ``likelihoods.SpecAbelLikelihood``)."""
+    A, cosT: the geometry matrices TRANSPOSED to [n,m] (see ``likelihoods.SpecAbelLikelihood``).
+    ``dlam``: spacing of ``lam`` when it is a uniform grid (recurrence kernels), 0 for arbitrary wavelengths."""
     F = _chk(F, "F"); A = _chk(A, "A"); cosT = _chk(cosT, "cosT"); lam = _chk(lam, "lam")
     _, S, n = F.shape
     m, k = A.shape[1], lam.numel()
     P = torch.empty((S, k, m), dtype=torch.float64, device=F.device)
-    rc = _capi.lib().gpinv_spec_fwd_f64(_p(F), _p(A), _p(cosT), _p(lam), None, n, m, k, S, _p(P), None, _st())
+    rc = _capi.lib().gpinv_spec_fwd_f64(_p(F), _p(A), _p(cosT), _p(lam), None, n, m, k, S, float(dlam), _p(P), None,
+                                        _st())
     _capi.check(rc, "spec_fwd")
     return P
 
 
 @torch.library.custom_op("gpinv::spec_resid", mutates_args=(), device_types="cuda")
-def spec_resid(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, Y: Tensor) -> Tuple[Tensor, Tensor]:
+def spec_resid(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, Y: Tensor, dlam: float = 0.0) -> Tuple[Tensor, Tensor]:
     """(sum (P - Y)^2 [1], P [S,k,m]); A, cosT transposed to [n,m]."""
     F = _chk(F, "F"); A = _chk(A, "A"); cosT = _chk(cosT, "cosT"); lam = _chk(lam, "lam"); Y = _chk(Y, "Y")
     _, S, n = F.shape
     m, k = A.shape[1], lam.numel()
     P = torch.empty((S, k, m), dtype=torch.float64, device=F.device)
     ss = torch.empty(1, dtype=torch.float64, device=F.device)
-    rc = _capi.lib().gpinv_spec_fwd_f64(_p(F), _p(A), _p(cosT), _p(lam), _p(Y), n, m, k, S, _p(P), _p(ss), _st())
+    rc = _capi.lib().gpinv_spec_fwd_f64(_p(F), _p(A), _p(cosT), _p(lam), _p(Y), n, m, k, S, float(dlam), _p(P),
+                                        _p(ss), _st())
     _capi.check(rc, "spec_fwd")
     return ss, P
 
 
 @torch.library.custom_op("gpinv::spec_bwd", mutates_args=(), device_types="cuda")
-def spec_bwd(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, Y: Tensor, P: Tensor, coef: Tensor) -> Tensor:
+def spec_bwd(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, Y: Tensor, P: Tensor, coef: Tensor,
+             dlam: float = 0.0) -> Tensor:
     F = _chk(F, "F"); P = _chk(P, "P"); coef = _chk(coef, "coef")
     _, S, n = F.shape
     m, k = A.shape[1], lam.numel()
     out = torch.empty_like(F)
     rc = _capi.lib().gpinv_spec_bwd_f64(_p(F), _p(A), _p(cosT), _p(lam), _p(Y), _p(P), _p(coef), n, m, k, S,
-                                        _p(out), _st())
+                                        float(dlam), _p(out), _st())
     _capi.check(rc, "spec_bwd")
     return out
 
 
 def _spec_setup(ctx, inputs, output):
-    F, A, cosT, lam, Y = inputs
+    F, A, cosT, lam, Y, dlam = inputs
     ctx.save_for_backward(F, A, cosT, lam, Y, output[1])
+    ctx.dlam = dlam
     ctx.set_materialize_grads(False)
 
 
 def _spec_backward(ctx, g_ss, g_p_unused):
     F, A, cosT, lam, Y, P = ctx.saved_tensors
     if g_ss is None:
-        return None, None, None, None, None
-    return spec_bwd(F, A, cosT, lam, Y, P, (2.0 * g_ss).reshape(1).contiguous()), None, None, None, None
+        return None, None, None, None, None, None
+    return spec_bwd(F, A, cosT, lam, Y, P, (2.0 * g_ss).reshape(1).contiguous(), ctx.dlam), None, None, None, None, None
 
 
 spec_resid.register_autograd(_spec_backward, setup_context=_spec_setup)

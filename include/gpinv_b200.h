@@ -87,6 +87,13 @@ int gpinv_potrf_bwd_f64(const double* L, int ldl, double* Abar, int ldab, int n,
 size_t gpinv_chol_core_ws_bytes(int n, int D);
 int gpinv_chol_core_f64(const double* X, int n, int D, int ldx, const double* ls, int ard, int mode,
                         double jitter, double* L, int ldl, int* info, void* ws, void* stream);
+/* The same with W = L^-1 (Winv [n,n]; scratch [n,n]) built alongside: row block by row block inside the
+ * factorisation on a low-priority stream of the library (n > 512), else right behind it on the side stream.  The
+ * inverse is what the reverse pass (gpinv_chol_core_bwd2_f64) multiplies with; `stream` does NOT wait for it:
+ * order a stream after it with gpinv_trtri_side_join. */
+int gpinv_chol_core_inv_f64(const double* X, int n, int D, int ldx, const double* ls, int ard, int mode,
+                            double jitter, double* L, int ldl, int* info, double* Winv, double* scratch, void* ws,
+                            void* stream);
 size_t gpinv_chol_core_bwd_ws_bytes(int n, int D);
 int gpinv_chol_core_bwd_f64(const double* X, int n, int D, int ldx, const double* ls, int ard,
                             int mode, const double* L, int ldl, const double* Lbar, int ldlb,
@@ -185,15 +192,17 @@ int gpinv_abel_bwd_f64(const double* Rs, const double* A, int lda, const double*
 /* --- T16: spectroscopic Abel transform (notebooks/Spectroscopic_Abel_inversion.ipynb:316-356).
  * F [3,S,n] = (log a, log sigma, v); At, cosTt: the notebook's [m,n] geometry matrices TRANSPOSED to
  * [n,m] (chord index contiguous, so that every access of both kernels is coalesced); lam [k];
- * Y [k,m] (may be NULL with sumsq); n <= 9000.
+ * Y [k,m] (may be NULL with sumsq); n <= 9000.  dlam: spacing of the wavelength grid when it is uniform
+ * (lam_k = lam_0 + k dlam, the notebook's np.linspace) -- the Gaussian line shape is then advanced along k by
+ * a two-term recurrence restarted every 16 wavelengths instead of one exp per term -- or 0 for arbitrary lam.
  * fwd: P [S,k,m] (may be NULL), *sumsq = sum (P - Y)^2 (may be NULL);
  * bwd: Fbar [3,S,n] = coef * sum_{k,m} (P - Y) dP/dF, coef a device scalar. */
 int gpinv_spec_fwd_f64(const double* F, const double* At, const double* cosTt, const double* lam,
-                       const double* Y, int n, int m, int k, int S, double* P, double* sumsq,
+                       const double* Y, int n, int m, int k, int S, double dlam, double* P, double* sumsq,
                        void* stream);
 int gpinv_spec_bwd_f64(const double* F, const double* At, const double* cosTt, const double* lam,
                        const double* Y, const double* P, const double* coef, int n, int m, int k,
-                       int S, double* Fbar, void* stream);
+                       int S, double dlam, double* Fbar, void* stream);
 
 /* --- T19 and its reverse: the optimiser's packed free state x (GPflow sorted_params order; the x of
  * GPinv/model.py:64-75) <-> constrained parameter blocks.  Block b covers x[off[b], off[b+1]);

@@ -223,6 +223,25 @@ def check_liks():
         report("spec_resid sumsq", rel(ss, ref.reshape(1)), 1e-13)
         report("spec_resid bwd", rel(gout, gref), 1e-12)
         report("spec_transform", rel(ops.spec_transform(t(F), t(A.T.copy()), t(cosT.T.copy()), t(lam)), Pref), 1e-13)
+        # uniform wavelength grid: the recurrence kernels (restart every 16 wavelengths), normal line widths and
+        # lines narrower than the grid spacing (direct evaluation per radial point), k not a multiple of 16
+        for width, tag in ((-0.5, "wide lines"), (-5.0, "narrow lines -> direct path"), (-2.2, "mixed")):
+            lam_u = np.linspace(-2.0, 2.5, k)
+            dl = float((lam_u[-1] - lam_u[0]) / (k - 1))
+            Fu = F.copy()
+            Fu[1] = width + (1.5 if tag == "mixed" else 0.2) * rng.randn(S, n)
+            Fut = torch.tensor(Fu, requires_grad=True)
+            Pr = O.spec_abel_transform(Fut.permute(1, 2, 0), torch.tensor(A), torch.tensor(cosT), torch.tensor(lam_u))
+            rr = ((Pr - torch.tensor(y)[None]) ** 2).sum()
+            (gr,) = torch.autograd.grad(rr, Fut)
+            Fud = t(Fu).requires_grad_(True)
+            ss, P = ops.spec_resid(Fud, t(A.T.copy()), t(cosT.T.copy()), t(lam_u), t(y), dl)
+            (go,) = torch.autograd.grad(ss.sum(), Fud)
+            report("spec recurrence P (%s) n=%d m=%d k=%d" % (tag, n, m, k), rel(P, Pr), 1e-12)
+            report("spec recurrence sumsq (%s)" % tag, rel(ss, rr.reshape(1)), 1e-12)
+            report("spec recurrence bwd (%s)" % tag, rel(go, gr), 1e-11)
+            report("spec recurrence transform (%s)" % tag,
+                   rel(ops.spec_transform(t(Fu), t(A.T.copy()), t(cosT.T.copy()), t(lam_u), dl), Pr), 1e-12)
     x = rng.randn(100001)
     report("sumsq", rel(ops.sumsq(t(x)), torch.tensor([np.sum(x * x)])), 1e-13)
 

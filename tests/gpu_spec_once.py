@@ -14,9 +14,12 @@ cosTt = torch.rand(n, m, dtype=torch.float64, device=dev, generator=g) * 2 - 1
 lam = torch.linspace(-3, 3, k, dtype=torch.float64, device=dev)
 Y = torch.rand(k, m, dtype=torch.float64, device=dev, generator=g)
 one = torch.ones(1, dtype=torch.float64, device=dev)
+dl = float((lam[-1] - lam[0]).item() / (k - 1))       # uniform grid: recurrence kernels (0.0 -> one exp per term)
+if len(sys.argv) > 1 and sys.argv[1] == "direct":
+    dl = 0.0
 for _ in range(3):
-    ss, P = ops.spec_resid(F, At, cosTt, lam, Y)
-    Fbar = ops.spec_bwd(F, At, cosTt, lam, Y, P, one)
+    ss, P = ops.spec_resid(F, At, cosTt, lam, Y, dl)
+    Fbar = ops.spec_bwd(F, At, cosTt, lam, Y, P, one, dl)
 torch.cuda.synchronize()
 
 
@@ -30,9 +33,9 @@ def timeit(fn, reps=50):
     return a.elapsed_time(b) / reps * 1e-3
 
 
-tf = timeit(lambda: ops.spec_resid(F, At, cosTt, lam, Y))
-tb = timeit(lambda: ops.spec_bwd(F, At, cosTt, lam, Y, P, one))
+tf = timeit(lambda: ops.spec_resid(F, At, cosTt, lam, Y, dl))
+tb = timeit(lambda: ops.spec_bwd(F, At, cosTt, lam, Y, P, one, dl))
 nexp = float(S) * k * m * n
-print("spec fwd %.1f us  (%.2f G exp/s)   spec bwd %.1f us  (%.2f G exp-terms/s)   [%d x %d x %d x %d = %.3g exponentials]"
-      % (tf * 1e6, nexp / tf / 1e9, tb * 1e6, nexp / tb / 1e9, S, k, m, n, nexp))
+print("dlam = %g:  spec fwd %.1f us  (%.2f G exp/s)   spec bwd %.1f us  (%.2f G exp-terms/s)   [%d x %d x %d x %d = %.3g exponentials]"
+      % (dl, tf * 1e6, nexp / tf / 1e9, tb * 1e6, nexp / tb / 1e9, S, k, m, n, nexp))
 print("ok", float(ss.item()), float(Fbar.abs().sum().item()))
