@@ -544,7 +544,7 @@ class Model(Parameterized):
                 # gather (pageable -> pinned, multi-threaded, GIL released) and per-block DMA are
                 # pipelined inside one native call
                 from . import _capi
-                nthr = max(1, min(8, torch.get_num_threads()))
+                nthr = max(1, min(int(os.environ.get("GPINV_UPLOAD_THREADS", "8")), torch.get_num_threads()))
                 rc = _capi.lib().gpinv_upload_tril_blocks_f64(
                     x.ctypes.data + 8 * b0, nq, rb, hin.data_ptr() + 8 * b0, dstage.data_ptr(),
                     offs_np.ctypes.data, take_np.ctypes.data, len(blocks), nthr,
@@ -769,7 +769,7 @@ class Model(Parameterized):
         with torch.cuda.stream(cs):
             if ctx is not None:
                 st["dstage"].zero_()
-            nthr = max(1, min(8, torch.get_num_threads()))
+            nthr = max(1, min(int(os.environ.get("GPINV_UPLOAD_THREADS", "8")), torch.get_num_threads()))
             rc = _capi.lib().gpinv_upload_tril_blocks_f64(
                 x.ctypes.data + 8 * b0, nq, st["rb"], hin.data_ptr() + 8 * b0, st["dstage"].data_ptr(),
                 st["offs_np"].ctypes.data, st["take_np"].ctypes.data, len(st["blocks"]), nthr, cs.cuda_stream)
@@ -885,6 +885,7 @@ class Model(Parameterized):
                 del later[:]
 
         active = [None]
+        ops.SIDE_PENDING[0] = False         # (a join inside the capture may only wait for work forked inside it)
         torch.cuda.synchronize()
         cap = torch.cuda.Stream()
         gc.collect()

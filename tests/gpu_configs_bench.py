@@ -26,8 +26,10 @@ def time_gpu(m, x, eps, iters):
     b.record()
     torch.cuda.synchronize()
     t_dev = a.elapsed_time(b) / iters / 1e3
-    kw = {} if eps is None else {"eps": eps}
-    m._objective(x, **kw)
+    # host API: numpy x in, (float, numpy gradient) out; the fixed draws (an extension of the reference's API, which
+    # draws inside the graph) stay on the device -- re-uploading 50 MB of eps per call is not part of the path
+    for _ in range(3):
+        m._objective(x, **kw)
     t0 = time.perf_counter()
     for _ in range(max(3, iters // 4)):
         m._objective(x, **kw)
