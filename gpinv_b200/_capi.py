@@ -40,6 +40,7 @@ SIGNATURES = {
     "gpinv_chol_core_f64": (_I, [_P, _I, _I, _I, _P, _I, _I, _D, _P, _I, _P, _P, _P]),
     "gpinv_chol_core_bwd_ws_bytes": (_Z, [_I, _I]),
     "gpinv_chol_core_bwd_f64": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
+    "gpinv_trtri_side_shard_f64": (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),
     "gpinv_chol_core_inv_f64": (_I, [_P, _I, _I, _I, _P, _I, _I, _D, _P, _I, _P, _P, _P, _P, _P]),
     "gpinv_chol_core_bwd2_f64": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P]),
     "gpinv_trtri_side_f64": (_I, [_P, _I, _P, _P, _I, _P]),

@@ -31,6 +31,7 @@ int potrf_bwd_hybrid_block();
 int potrf_bwd_hybrid_ex_f64(const double*, int, double*, int, int, double*, int, int, cudaStream_t,
                             const double* W_pre = nullptr);
 int trtri_side_f64(const double*, int, double*, double*, int, cudaStream_t);
+int trtri_side_shard_f64(const double*, int, double*, double*, int, int, int, cudaStream_t);
 int trtri_side_join_f64(cudaStream_t);
 int trtri_side_sync_f64();
 int potrf_ex_f64(double*, int, int, int*, int, cudaStream_t, double* Winv = nullptr, double* Tinv = nullptr,
@@ -246,6 +247,12 @@ int gpinv_chol_core_inv_f64(const double* X, int n, int D, int ldx, const double
 int gpinv_trtri_side_f64(const double* L, int ldl, double* Winv, double* scratch, int n, void* stream) {
   if (n <= 0 || ldl < n || !Winv || !scratch) return GPINV_ERR_ARG;
   return trtri_side_f64(L, ldl, Winv, scratch, n, ST(stream));
+}
+
+int gpinv_trtri_side_shard_f64(const double* L, int ldl, double* Winv, double* scratch, int n, int rank, int G,
+                               void* stream) {
+  if (n <= 0 || ldl < n || !Winv || !scratch) return GPINV_ERR_ARG;
+  return trtri_side_shard_f64(L, ldl, Winv, scratch, n, rank, G, ST(stream));
 }
 
 int gpinv_trtri_side_join(void* stream) { return trtri_side_join_f64(ST(stream)); }

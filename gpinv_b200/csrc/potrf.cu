@@ -404,7 +404,7 @@ static int pick_splitk(int M, int N, int K, bool lower) {
 }
 
 static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cudaStream_t st, int stop = 0x7fffffff,
-                     int ws_slot = 0, int ldw = 0);
+                     int ws_slot = 0, int ldw = 0, int top_rank = -1, int top_G = 0);
 
 // Side stream + events for the look-ahead (one set per device, created on first use).
 struct LookAhead {
@@ -824,8 +824,12 @@ __global__ void mirror_lower_kernel(double* __restrict__ A, int n, int ld) {
 // W (n x n, ld = n, zero on entry) <- L^{-1};  T: n x n scratch.
 // With `stop` < n only the diagonal blocks of size `stop` (a power-of-two multiple of NB, blocks
 // aligned at multiples of `stop`) are inverted; the rest of W stays zero.
+// top_G > 1 (sample sharding over top_G GPUs, n = 2 s_top): the LAST merge level -- W21 = -W22 L21 W11 with
+// s_top = n / 2, three quarters of the inversion's flops -- is computed for this rank's column slices of W21
+// only (2 top_G slices of width s_top / 2 top_G, rank r owns slices r and 2 top_G - 1 - r: the triangular k
+// range of the first product makes early slices dearer, pairing evens it out); the caller all-gathers the slices.
 static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cudaStream_t st, int stop, int ws_slot,
-                     int ldw) {
+                     int ldw, int top_rank, int top_G) {
   if (ldw <= 0) ldw = n;        // W and T are n x n with leading dimension ldw
   using namespace pcfg;
   static bool attr_dev[64] = {};
@@ -845,6 +849,21 @@ static int trtri_f64(const double* L, int ldl, double* W, double* T, int n, cuda
     while ((long long)(nfull + 1) * 2 * s <= n) ++nfull;
     const long long strL = (long long)2 * s * ldl + 2 * s;
     const long long strW = (long long)2 * s * ldw + 2 * s;
+    if (top_G > 1 && 2 * s == n && s % (4 * top_G) == 0) {
+      const int wsl = s / (2 * top_G);
+      for (int t = 0; t < 2; ++t) {
+        const int a = (t == 0 ? top_rank : 2 * top_G - 1 - top_rank) * wsl;      // first column of the slice
+        // T21[:, a:a+wsl] = L21[:, a:] W11[a:, a:a+wsl]      (rows < a of that column slice of W11 are zero)
+        rc = gemm_batched(LK, LMN, s, wsl, s - a, 1.0, L + (size_t)s * ldl + a, ldl, 0, W + (size_t)a * ldw + a, ldw, 0,
+                          0.0, T + (size_t)s * ldw + a, ldw, 0, 1, false, 2, st, 1, ws_slot);
+        if (rc) return rc;
+        // W21[:, a:a+wsl] = -W22 T21[:, a:a+wsl]
+        rc = gemm_batched(LK, LMN, s, wsl, s, -1.0, W + (size_t)s * ldw + s, ldw, 0, T + (size_t)s * ldw + a, ldw, 0,
+                          0.0, W + (size_t)s * ldw + a, ldw, 0, 1, false, 3, st, 1, ws_slot);
+        if (rc) return rc;
+      }
+      continue;
+    }
     for (int pass = 0; pass < 2; ++pass) {
       const int i0 = pass == 0 ? 0 : nfull * 2 * s;
       const int batch = pass == 0 ? nfull : 1;
@@ -1167,13 +1186,21 @@ int potrf_bwd_hybrid_block() { return bwd_block(); }
 // so far (the factorisation) is done.  The inverse only depends on L, so it overlaps the sampling /
 // likelihood stages that follow on `st`; trtri_side_join_f64 makes a stream wait for it (the reverse
 // sweep calls it before its first use of W).  T: n x n scratch.  Split-K workspace half 1.
+int trtri_side_shard_f64(const double* L, int ldl, double* W, double* T, int n, int rank, int G, cudaStream_t st);
+
 int trtri_side_f64(const double* L, int ldl, double* W, double* T, int n, cudaStream_t st) {
+  return trtri_side_shard_f64(L, ldl, W, T, n, 0, 1, st);
+}
+
+// rank / G: see trtri_f64 (G = 1: the whole inverse)
+int trtri_side_shard_f64(const double* L, int ldl, double* W, double* T, int n, int rank, int G, cudaStream_t st) {
+  if (G < 1 || rank < 0 || rank >= G) return GPINV_ERR_ARG;
   LookAhead* la = lookahead_for_current_device();
   if (!la) return GPINV_ERR_CUDA;
   GPINV_TRY(cudaEventRecord(la->evF, st));
   GPINV_TRY(cudaStreamWaitEvent(la->side, la->evF, 0));
   GPINV_TRY(cudaMemsetAsync(W, 0, (size_t)n * n * sizeof(double), la->side));
-  int rc = trtri_f64(L, ldl, W, T, n, la->side, 0x7fffffff, 1);
+  int rc = trtri_f64(L, ldl, W, T, n, la->side, 0x7fffffff, 1, 0, rank, G);
   if (rc) return rc;
   GPINV_TRY(cudaEventRecord(la->evW, la->side));
   return GPINV_OK;

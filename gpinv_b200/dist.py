@@ -71,6 +71,14 @@ class DistContext(object):
             out.copy_(tmp.view(self.world_size, -1)[self.rank])
         return out
 
+    def all_gather(self, out, inp):
+        """out [G * inp.numel()] <- the ranks' inp, in rank order."""
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_gather_into_tensor(out, inp, group=self.group)
+        else:
+            dist.all_gather(list(out.view(self.world_size, -1).unbind(0)), inp.reshape(-1), group=self.group)
+        return out
+
     def all_reduce_async(self, buf):
         """Start the sum over ranks and return the work handle (``.wait()`` orders the caller's
         stream after it)."""

@@ -266,6 +266,7 @@ class Model(Parameterized):
         self._pending_infos = []
         col = ops.DeferredReverse(lambda nn: ctx.shard_width(nn) > 0)
         prev = ops.defer_reverse(col)
+        ops.INVERSE_SHARD = (ctx.rank, ctx.world_size)      # the inversion's last level: this rank's slices only
         try:
             with self.tensor_mode():
                 f = self.build_likelihood(**kw)
@@ -276,15 +277,17 @@ class Model(Parameterized):
             (gx,) = torch.autograd.grad(nf, [leaf], retain_graph=True, allow_unused=True)
         finally:
             ops.defer_reverse(prev)
+            ops.INVERSE_SHARD = None
             self.clear_tensors()
         n = x.numel()
         buf = self._grad_value_buffer(gx, nf, n, x.device)
         st.update(leaf=leaf, buf=buf, n=n, items=col.items, big=None, early=None, tri=0)
-        if col.items:
+        if ops.SIDE_PENDING[0]:
             ops.trtri_side_join()            # (inside a capture: the side stream must be joined before it ends)
         G = ctx.world_size
         st["rs_in"] = [ops.lbar_pack(it[5], G) for it in col.items]
         st["rs_out"] = [torch.empty(r.numel() // G, dtype=torch.float64, device=x.device) for r in st["rs_in"]]
+        self._inverse_slices_stage(st, col.items, ctx, x.device)
         params, offs, _codes = self.fused_layout()
         big = max(range(len(params)), key=lambda i: params[i].size)
         a, b = offs[big], offs[big + 1]
@@ -298,8 +301,34 @@ class Model(Parameterized):
             else:
                 st["early"] = buf[a:b]
 
+    @staticmethod
+    def _inverse_slices_stage(st, items, ctx, dev):
+        """Pack this rank's slices of every sharded inversion (ops.INVERSE_SHARD) for the all-gather."""
+        from . import ops
+        G = ctx.world_size
+        st["winv_in"], st["winv_out"], st["winv_W"] = [], [], []
+        for it in items:
+            W = it[4]
+            if W.numel() and ops.inverse_shardable(it[3].shape[0], G):
+                mine = ops.inverse_slices_pack(W, ctx.rank, G)
+                st["winv_in"].append(mine)
+                st["winv_out"].append(torch.empty(G * mine.numel(), dtype=torch.float64, device=dev))
+                st["winv_W"].append(W)
+
+    @staticmethod
+    def _inverse_slices_exchange(st, ctx):
+        for o, i in zip(st["winv_out"], st["winv_in"]):
+            ctx.all_gather(o, i)
+
+    @staticmethod
+    def _inverse_slices_finish(st, ctx):
+        from . import ops
+        for W, o in zip(st["winv_W"], st["winv_out"]):
+            ops.inverse_slices_unpack_(W, o, ctx.world_size)
+
     def _shard_exchange_1(self, st):
         ctx = self.dist
+        self._inverse_slices_exchange(st, ctx)
         for o, i in zip(st["rs_out"], st["rs_in"]):
             ctx.reduce_scatter(o, i)
         st["work"] = ctx.all_reduce_async(st["early"]) if st["big"] is not None else None
@@ -309,6 +338,7 @@ class Model(Parameterized):
         ctx = self.dist
         leaf, buf, n = st["leaf"], st["buf"], st["n"]
         gx2 = None
+        self._inverse_slices_finish(st, ctx)
         if st["items"]:
             outs, gs = [], []
             for (X, ls, mode, L, W, _lbar), dsh in zip(st["items"], st["rs_out"]):
@@ -785,6 +815,7 @@ class Model(Parameterized):
         st["g2"].replay()
         work = None
         if ctx is not None:
+            self._inverse_slices_exchange(st, ctx)
             for o_, i_ in zip(st["rs_out"], st["rs_in"]):
                 ctx.reduce_scatter(o_, i_)
             work = ctx.all_reduce_async(st["qc"])
@@ -894,6 +925,7 @@ class Model(Parameterized):
         prev = ops.defer_reverse(col)
         later = [] if ctx is not None else None
         ops.INVERSE_LATER = later
+        ops.INVERSE_SHARD = None if ctx is None else (ctx.rank, G)
         try:
             with torch.cuda.stream(cap):
                 g1.capture_begin(**mode)
@@ -920,16 +952,21 @@ class Model(Parameterized):
                     st["qc"] = ops.tri_compact(gb)
                 if ops.SIDE_PENDING[0]:
                     ops.trtri_side_join()
+                if ctx is not None:
+                    self._inverse_slices_stage(st, col.items, ctx, dev)
                 g2.capture_end()
                 active[0] = None
                 if ctx is not None:             # the ranks' NCCL call order stays aligned with the replay's
                     ctx.all_reduce(st["dstage"])
+                    self._inverse_slices_exchange(st, ctx)
                     for o_, i_ in zip(st["rs_out"], st["rs_in"]):
                         ctx.reduce_scatter(o_, i_)
                     ctx.all_reduce(st["qc"])
                 g3.capture_begin(pool=g1.pool(), **mode)
                 active[0] = g3
                 extra = None
+                if ctx is not None:
+                    self._inverse_slices_finish(st, ctx)
                 if col.items:
                     outs, gs = [], []
                     for k, (X_, ls_, mode_, L_, W_, lbar_) in enumerate(col.items):
@@ -966,6 +1003,7 @@ class Model(Parameterized):
         finally:
             ops.defer_reverse(prev)
             ops.INVERSE_LATER = None
+            ops.INVERSE_SHARD = None
             params[big]._before_use = None
             self.clear_tensors()
             if gc_was_on:

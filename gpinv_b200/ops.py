@@ -223,11 +223,14 @@ def chol_core(X: Tensor, ls: Tensor, mode: int, jitter: float, with_inverse: boo
         if not capturing and len(_W_KEEP) >= 4:
             _capi.check(lib.gpinv_trtri_side_sync(), "trtri_side_sync")      # idle unless a result was dropped
             del _W_KEEP[0]
-        if INVERSE_LATER is not None:
+        if INVERSE_LATER is not None or INVERSE_SHARD is not None:
             rc = lib.gpinv_chol_core_f64(_p(X), n, D, D, _p(ls), ard, mode, float(jitter), _p(Lm), n, _p(info),
                                          _p(ws), _st())
             _capi.check(rc, "chol_core")
-            INVERSE_LATER.append((Lm, W))        # the caller starts the inversion itself (start_inverse)
+            if INVERSE_LATER is not None:
+                INVERSE_LATER.append((Lm, W))    # the caller starts the inversion itself (start_inverse)
+            else:
+                start_inverse(Lm, W)
         else:
             # factorisation with the inversion interleaved (row blocks of W on a low-priority stream of the library)
             rc = lib.gpinv_chol_core_inv_f64(_p(X), n, D, D, _p(ls), ard, mode, float(jitter), _p(Lm), n, _p(info),
@@ -317,12 +320,47 @@ def _chol_core_backward(ctx, Lbar, _info_bar, _w_bar):
 INVERSE_LATER = None
 
 
+# None, or (rank, G) under sample sharding: the last merge level of every shardable inversion (three quarters of
+# its flops) is computed for this rank's column slices only; the caller all-gathers them (Model._shard_*).
+INVERSE_SHARD = None
+
+
+def inverse_shardable(n: int, G: int) -> bool:
+    """n = 64 * 2^k, large enough, and the slices of the last level are TMA-aligned."""
+    return G > 1 and n >= 1024 and (n & (n - 1)) == 0 and (n // 2) % (4 * G) == 0
+
+
 def start_inverse(Lm: Tensor, W: Tensor):
     """W[0] <- L^-1 on the library's side stream, behind the work already enqueued on the current stream."""
     n = Lm.shape[0]
-    _capi.check(_capi.lib().gpinv_trtri_side_f64(_p(Lm), n, _p(W), C.c_void_p(W.data_ptr() + 8 * n * n), n, _st()),
-                "trtri_side")
+    lib = _capi.lib()
+    scratch = C.c_void_p(W.data_ptr() + 8 * n * n)
+    if INVERSE_SHARD is not None and inverse_shardable(n, INVERSE_SHARD[1]):
+        _capi.check(lib.gpinv_trtri_side_shard_f64(_p(Lm), n, _p(W), scratch, n, INVERSE_SHARD[0], INVERSE_SHARD[1],
+                                                   _st()), "trtri_side_shard")
+    else:
+        _capi.check(lib.gpinv_trtri_side_f64(_p(Lm), n, _p(W), scratch, n, _st()), "trtri_side")
     SIDE_PENDING[0] = True
+
+
+def inverse_slices_pack(W: Tensor, rank: int, G: int) -> Tensor:
+    """This rank's two column slices of the bottom-left block of W[0] = L^-1 (see INVERSE_SHARD), [2, n/2, n/4G]."""
+    n = W.shape[1]
+    s, w = n // 2, n // (4 * G)
+    blk = W[0][s:, :s]
+    return torch.stack([blk[:, rank * w:(rank + 1) * w], blk[:, (2 * G - 1 - rank) * w:(2 * G - rank) * w]])
+
+
+def inverse_slices_unpack_(W: Tensor, gathered: Tensor, G: int) -> None:
+    """Write the all-gathered slices [G, 2, n/2, n/4G] into the bottom-left block of W[0]."""
+    n = W.shape[1]
+    s, w = n // 2, n // (4 * G)
+    blk = W[0][s:, :s]
+    src = gathered.reshape(G, 2, s, w)
+    for g in range(G):                     # (plain strided copies: nothing here needs a host-built index tensor,
+        for t in (0, 1):                   #  so it can sit inside a CUDA-graph capture)
+            i = g if t == 0 else 2 * G - 1 - g
+            blk[:, i * w:(i + 1) * w].copy_(src[g, t])
 
 
 def trtri_side_join():

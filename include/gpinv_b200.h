@@ -110,6 +110,12 @@ int gpinv_chol_core_bwd2_f64(const double* X, int n, int D, int ldx, const doubl
  * gpinv_trtri_side_join makes `stream` wait for the most recent such inversion. */
 int gpinv_trtri_side_f64(const double* L, int ldl, double* Winv, double* scratch, int n, void* stream);
 int gpinv_trtri_side_join(void* stream);
+/* Sample sharding over G GPUs, n = 64 * 2^k with (n/2) % 4G == 0: like gpinv_trtri_side_f64, but the last merge
+ * level of the inversion, W21 = -W22 L21 W11 with blocks of n/2 (three quarters of its flops), is computed for
+ * this rank's column slices of W21 only: 2G slices of width n / 4G, rank r owns slices r and 2G-1-r.  The other
+ * slices of Winv[n/2:, :n/2] stay zero; the caller all-gathers them (gpinv_b200/dist.py). */
+int gpinv_trtri_side_shard_f64(const double* L, int ldl, double* Winv, double* scratch, int n, int rank, int G,
+                               void* stream);
 /* host-side wait for the side stream (before an inverse buffer is recycled outside a reverse pass) */
 int gpinv_trtri_side_sync(void);
 /* --- T22: X <- X L^{-T} (row-wise forward substitution; X is m x n).  Replaces

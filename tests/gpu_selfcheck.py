@@ -371,6 +371,31 @@ def check_shard():
                 c0s = [r * w, (2 * G - 1 - r) * w]
                 tot += ops.chol_core_bwd_shard(x, ls, 1, L, W, chunks[r].contiguous(), w, c0s)
             report("chol_core_bwd_shard n=%d G=%d (sum of shares vs replicated)" % (n, G), rel(tot, ref), 1e-7)
+    # sharded last level of the inversion: G emulated ranks, their slices gathered, against the whole inverse
+    for n, Gs in ((1024, (2, 4, 8)), (2048, (2, 8))):
+        x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)[:, None]
+        ls = t([0.3])
+        L, info, Wfull = ops.chol_core(x, ls, 1, 1e-6, True)
+        ops.trtri_side_join()
+        for G in Gs:
+            assert ops.inverse_shardable(n, G)
+            Ws, packs = [], []
+            for r in range(G):
+                W = torch.empty((2, n, n), dtype=torch.float64, device=dev)
+                ops.INVERSE_SHARD = (r, G)
+                try:
+                    ops.start_inverse(L, W)
+                finally:
+                    ops.INVERSE_SHARD = None
+                ops.trtri_side_join()
+                Ws.append(W)
+                packs.append(ops.inverse_slices_pack(W, r, G))
+            gathered = torch.stack(packs).reshape(-1)
+            worst = 0.0
+            for r in range(G):
+                ops.inverse_slices_unpack_(Ws[r], gathered, G)
+                worst = max(worst, rel(Ws[r][0], Wfull[0]))
+            report("sharded inversion n=%d G=%d (every rank's W vs the whole inverse)" % (n, G), worst, 1e-12)
     for n in (1, 7, 300, 1024):
         M = t(np.random.RandomState(n).randn(n, n))
         c = ops.tri_compact(M)
