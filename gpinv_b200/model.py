@@ -415,11 +415,32 @@ class Model(Parameterized):
             self._graphs[key] = ent
         gA, gB, gC, sx, sdyn, st, f, g, infos, _keep = ent
         self._graph_refresh(sx, sdyn, x, dyn)
+        trace = os.environ.get("GPINV_SHARD_TRACE")
+        if trace:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            ev[0].record()
         gA.replay()
+        if trace:
+            ev[1].record()
         self._shard_exchange_1(st)
+        if trace:
+            ev[2].record()
         gB.replay()
+        if trace:
+            ev[3].record()
         self._shard_exchange_2(st)
+        if trace:
+            ev[4].record()
         gC.replay()
+        if trace:
+            ev[5].record()
+            torch.cuda.synchronize()
+            acc = self.__dict__.setdefault("_shard_trace", [])
+            acc.append([ev[i].elapsed_time(ev[i + 1]) for i in range(5)])
+            if len(acc) == int(trace):
+                m_ = np.mean(np.array(acc[2:]), axis=0)
+                print("shard-trace rank %d (ms): stage A %.3f | exchange 1 (blocking part) %.3f | stage B %.3f | exchange 2 %.3f | "
+                      "stage C %.3f | sum %.3f" % ((self.dist.rank,) + tuple(m_) + (float(m_.sum()),)), file=sys.stderr, flush=True)
         self._pending_infos = list(infos)
         return f, g
 

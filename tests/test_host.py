@@ -301,6 +301,11 @@ want = float(np.sum(0.5 * (S + S.T) * dK))
 ok = abs(float(tot) - want) <= 1e-10 * abs(want)
 if not ok:
     print("rank %d: sharded %r replicated %r" % (rank, float(tot), want), flush=True)
+# all_gather (exchange of the sharded inversion's slices): rank order, every rank gets everything
+mine = torch.full((5,), float(rank), dtype=torch.float64)
+got = torch.empty(5 * world, dtype=torch.float64)
+ctx.all_gather(got, mine)
+ok = ok and bool(torch.equal(got.view(world, 5), torch.arange(world, dtype=torch.float64)[:, None].expand(world, 5)))
 dist.destroy_process_group()
 sys.exit(0 if ok else 3)
 '''
