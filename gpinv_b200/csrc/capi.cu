@@ -77,6 +77,8 @@ int kl_white_f64(const double*, const double*, int, int, int, double*, cudaStrea
 int kl_white_bwd_f64(const double*, const double*, int, int, int, const double*, double*, double*, cudaStream_t);
 int adam_step_f64(double*, double*, double*, const double*, long long, double, double, double, double, long long*,
                   cudaStream_t);
+int gauss_logp_f64(const double*, const double*, double, double*, cudaStream_t);
+int gauss_logp_bwd_f64(const double*, const double*, double, const double*, double*, double*, cudaStream_t);
 int spec_fwd_f64(const double*, const double*, const double*, const double*, const double*, int, int,
                  int, int, double, double*, double*, cudaStream_t);
 int spec_bwd_f64(const double*, const double*, const double*, const double*, const double*,
@@ -423,6 +425,16 @@ int gpinv_adam_step_f64(double* x, double* m, double* v, const double* g, long l
                         double beta1, double beta2, double epsilon, long long* step, void* stream) {
   if (!x || !m || !v || !g || !step) return GPINV_ERR_ARG;
   return adam_step_f64(x, m, v, g, count, lr, beta1, beta2, epsilon, step, ST(stream));
+}
+
+int gpinv_gauss_logp_f64(const double* ss, const double* var, double count, double* out, void* stream) {
+  if (!ss || !var || !out) return GPINV_ERR_ARG;
+  return gauss_logp_f64(ss, var, count, out, ST(stream));
+}
+int gpinv_gauss_logp_bwd_f64(const double* ss, const double* var, double count, const double* g, double* ss_bar,
+                             double* var_bar, void* stream) {
+  if (!ss || !var || !g || !ss_bar || !var_bar) return GPINV_ERR_ARG;
+  return gauss_logp_bwd_f64(ss, var, count, g, ss_bar, var_bar, ST(stream));
 }
 
 int gpinv_lbar_pack_f64(const double* Lbar, int ldlb, int n, int w, int G, double* out, void* stream) {

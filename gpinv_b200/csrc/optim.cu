@@ -272,4 +272,35 @@ int adam_step_f64(double* x, double* m, double* v, const double* g, long long co
   return GPINV_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Gaussian log-density summed over `count` observations from the residual sum of squares (GPflow
+// densities.gaussian behind GPinv/likelihoods.py:70-76 and the notebooks' likelihoods):
+//   out = -count/2 (log 2 pi + log var) - ss / (2 var)
+// and its reverse  ss_bar = -g / (2 var),  var_bar = g (-count / (2 var) + ss / (2 var^2)).
+// One thread each: these replace ~15 scalar elementwise launches of the ELBO assembly.
+// ---------------------------------------------------------------------------------------
+__global__ void gauss_logp_kernel(const double* __restrict__ ss, const double* __restrict__ var, double count,
+                                  double* __restrict__ out) {
+  const double v = var[0];
+  out[0] = -0.5 * count * (1.8378770664093453 + log(v)) - 0.5 * ss[0] / v;
+}
+__global__ void gauss_logp_bwd_kernel(const double* __restrict__ ss, const double* __restrict__ var, double count,
+                                      const double* __restrict__ g, double* __restrict__ ss_bar,
+                                      double* __restrict__ var_bar) {
+  const double v = var[0], gg = g[0];
+  ss_bar[0] = -0.5 * gg / v;
+  var_bar[0] = gg * (-0.5 * count / v + 0.5 * ss[0] / (v * v));
+}
+int gauss_logp_f64(const double* ss, const double* var, double count, double* out, cudaStream_t st) {
+  gauss_logp_kernel<<<1, 1, 0, st>>>(ss, var, count, out);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+int gauss_logp_bwd_f64(const double* ss, const double* var, double count, const double* g, double* ss_bar,
+                       double* var_bar, cudaStream_t st) {
+  gauss_logp_bwd_kernel<<<1, 1, 0, st>>>(ss, var, count, g, ss_bar, var_bar);
+  GPINV_CHECK_LAUNCH();
+  return GPINV_OK;
+}
+
 }  // namespace gpinv

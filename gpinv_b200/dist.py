@@ -111,6 +111,9 @@ class SharedHostBuffers(object):
         fd = -1
         try:
             if ctx.rank == 0:
+                vfs = os.statvfs("/dev/shm")
+                if vfs.f_bavail * vfs.f_frsize < nbytes + (64 << 20):
+                    raise OSError("not enough room in /dev/shm")     # (a sparse file would SIGBUS on first touch)
                 fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
                 os.ftruncate(fd, nbytes)     # zero-filled
         except OSError:

@@ -59,8 +59,7 @@ class Gaussian(Likelihood):
     def logp_sum(self, F, Y, expF=None):
         var = self.variance
         ss = ops.gauss_sumsq(_internal(F), Y.contiguous())
-        cnt = float(F.numel())
-        return -0.5 * cnt * (LOG2PI + torch.log(var)) - 0.5 * ss / var
+        return ops.gauss_logp(ss, var, float(F.numel())).reshape(())
 
     def sample_F(self, F):
         return F
@@ -90,8 +89,7 @@ class AbelLikelihood(Likelihood):
         Ei = torch.exp(Fi).detach() if expF is None else _internal(expF)[0]
         ss, _ = ops.abel_resid(Fi, Ei, self.Amat, Y.reshape(-1).contiguous())
         var = self.variance
-        cnt = float(F.shape[0] * self.Amat.shape[0])
-        return -0.5 * cnt * (LOG2PI + torch.log(var)) - 0.5 * ss / var
+        return ops.gauss_logp(ss, var, float(F.shape[0] * self.Amat.shape[0])).reshape(())
 
     def sample_F(self, F):
         X = torch.exp(F[:, :, 0]).contiguous()               # [S,n]
@@ -163,7 +161,7 @@ class SpecAbelLikelihood(Likelihood):
         At, cTt = self._geometry_T()
         ss, P = ops.spec_resid(_internal(F), At, cTt, self.lam.reshape(-1).contiguous(), Y.contiguous(), self._dlam())
         var = self.variance
-        return -0.5 * float(P.numel()) * (LOG2PI + torch.log(var)) - 0.5 * ss / var
+        return ops.gauss_logp(ss, var, float(P.numel())).reshape(())
 
     def sample_Y(self, F, noise=None):
         f = self.sample_F(F)

@@ -1034,7 +1034,12 @@ class Model(Parameterized):
         st["g1"], st["g2"], st["g3"] = g1, g2, g3
         if ctx is not None and os.environ.get("GPINV_SHARED_RESULT", "1") != "0":
             from .dist import SharedHostBuffers
-            st["shared"] = SharedHostBuffers(ctx, n + 1)
+            try:
+                st["shared"] = SharedHostBuffers(ctx, n + 1)
+            except RuntimeError as e:       # raised on every rank together: per-rank result buffers instead
+                if ctx.rank == 0:
+                    print("gpinv_b200: %s; every rank downloads the whole gradient" % e, file=sys.stderr)
+                st["shared"] = None
         st["infos"] = list(self._pending_infos)
         st["keep"] = [d._tensor for nd in self._all_parameterized() for d in nd.data_holders] + \
                      [p._fixed_dev for p in self.all_params() if p.fixed]

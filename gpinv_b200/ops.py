@@ -733,6 +733,45 @@ def sumsq(x: Tensor) -> Tensor:
 
 # --------------------------------------------------------------------------------------
 # T16 spectroscopic Abel transform
+@torch.library.custom_op("gpinv::gauss_logp", mutates_args=(), device_types="cuda")
+def gauss_logp(ss: Tensor, var: Tensor, count: float) -> Tensor:
+    """-count/2 (log 2 pi + log var) - ss / (2 var) as a device scalar [1]: the Gaussian log-density summed over
+    `count` observations, from the residual sum of squares (GPflow densities.gaussian)."""
+    ss = _chk(ss, "ss").reshape(1)
+    var = _chk(var, "var").reshape(1)
+    out = torch.empty(1, dtype=torch.float64, device=ss.device)
+    _capi.check(_capi.lib().gpinv_gauss_logp_f64(_p(ss), _p(var), float(count), _p(out), _st()), "gauss_logp")
+    return out
+
+
+@torch.library.custom_op("gpinv::gauss_logp_bwd", mutates_args=(), device_types="cuda")
+def gauss_logp_bwd(ss: Tensor, var: Tensor, count: float, g: Tensor) -> List[Tensor]:
+    ss = _chk(ss, "ss").reshape(1)
+    var = _chk(var, "var").reshape(1)
+    g = _chk(g, "g").reshape(1)
+    ss_bar = torch.empty(1, dtype=torch.float64, device=ss.device)
+    var_bar = torch.empty(1, dtype=torch.float64, device=ss.device)
+    _capi.check(_capi.lib().gpinv_gauss_logp_bwd_f64(_p(ss), _p(var), float(count), _p(g), _p(ss_bar), _p(var_bar),
+                                                     _st()), "gauss_logp_bwd")
+    return [ss_bar, var_bar]
+
+
+def _glp_setup(ctx, inputs, output):
+    ss, var, count = inputs
+    ctx.save_for_backward(ss, var)
+    ctx.count = count
+    ctx.shapes = (ss.shape, var.shape)
+
+
+def _glp_backward(ctx, g):
+    ss, var = ctx.saved_tensors
+    ss_bar, var_bar = gauss_logp_bwd(ss, var, ctx.count, g.contiguous())
+    return ss_bar.reshape(ctx.shapes[0]), var_bar.reshape(ctx.shapes[1]), None
+
+
+gauss_logp.register_autograd(_glp_backward, setup_context=_glp_setup)
+
+
 # --------------------------------------------------------------------------------------
 @torch.library.custom_op("gpinv::spec_transform", mutates_args=(), device_types="cuda")
 def spec_transform(F: Tensor, A: Tensor, cosT: Tensor, lam: Tensor, dlam: float = 0.0) -> Tensor:

@@ -231,6 +231,14 @@ int gpinv_kl_white_f64(const double* q_mu, const double* q_sqrt, int n, int R, i
 int gpinv_kl_white_bwd_f64(const double* q_mu, const double* q_sqrt, int n, int R, int q_diag,
                            const double* gbar, double* mu_bar, double* q_bar, void* stream);
 
+/* --- Gaussian log-density from the residual sum of squares (GPflow densities.gaussian behind
+ * GPinv/likelihoods.py:70-76 and the notebooks' Abel / spectroscopic likelihoods), all device scalars:
+ * out = -count/2 (log 2 pi + log var) - ss / (2 var);  reverse: ss_bar = -g / (2 var),
+ * var_bar = g (-count / (2 var) + ss / (2 var^2)). */
+int gpinv_gauss_logp_f64(const double* ss, const double* var, double count, double* out, void* stream);
+int gpinv_gauss_logp_bwd_f64(const double* ss, const double* var, double count, const double* g, double* ss_bar,
+                             double* var_bar, void* stream);
+
 /* --- optimiser step of the training loop (GPinv/model.py:206-240 drives a tf.train optimiser;
  * testing/test_stvgp.py:31-35: tf.train.AdamOptimizer).  TensorFlow's Adam update in place on the
  * device-resident state: t = step + 1; lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t);

@@ -244,6 +244,17 @@ def check_liks():
                    rel(ops.spec_transform(t(Fu), t(A.T.copy()), t(cosT.T.copy()), t(lam_u), dl), Pr), 1e-12)
     x = rng.randn(100001)
     report("sumsq", rel(ops.sumsq(t(x)), torch.tensor([np.sum(x * x)])), 1e-13)
+    # fused Gaussian log-density from the residual sum of squares, and its reverse
+    for ssv, varv, cnt in ((123.4, 0.37, 4096.0), (5.0e7, 2.5, 8388608.0)):
+        sst = torch.tensor([ssv], dtype=torch.float64, requires_grad=True)
+        vt = torch.tensor([varv], dtype=torch.float64, requires_grad=True)
+        ref = -0.5 * cnt * (np.log(2 * np.pi) + torch.log(vt)) - 0.5 * sst / vt
+        gs, gv = torch.autograd.grad((3.0 * ref).sum(), [sst, vt])
+        ssd, vd = t([ssv]).requires_grad_(True), t([varv]).requires_grad_(True)
+        out = ops.gauss_logp(ssd, vd, cnt)
+        g1, g2 = torch.autograd.grad((3.0 * out).sum(), [ssd, vd])
+        report("gauss_logp value", rel(out, ref), 1e-15)
+        report("gauss_logp d/dss, d/dvar", max(rel(g1, gs), rel(g2, gv)), 1e-14)
 
 
 def check_kron():
