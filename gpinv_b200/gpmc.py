@@ -64,13 +64,15 @@ class GPMC(GPModel):
         eps = torch.zeros((R, 1, n), dtype=torch.float64, device=dev)
         Fs, Es = [], []
         for core, r0, r1 in chol.groups():
+            def part(t, r0=r0, r1=r1):       # (no slices when one group covers every latent function: see StVGP._sample)
+                return t if (r0 == 0 and r1 == t.shape[0]) else t[r0:r1]
             if chol.kron:
                 from . import kronecker
-                F, expF, _ = kronecker.kron_sample(core, chol.sqrt_var[r0:r1], ones[r0:r1], V[r0:r1],
-                                                   mean[r0:r1], eps[r0:r1], True, want_exp)
+                F, expF, _ = kronecker.kron_sample(core, part(chol.sqrt_var), part(ones), part(V),
+                                                   part(mean), part(eps), True, want_exp)
             else:
-                F, expF, _, _ = ops.stvgp_sample(core, chol.sqrt_var[r0:r1].contiguous(), ones[r0:r1],
-                                                 V[r0:r1], mean[r0:r1], eps[r0:r1], True, want_exp)
+                F, expF, _, _ = ops.stvgp_sample(core, part(chol.sqrt_var).contiguous(), part(ones),
+                                                 part(V), part(mean), part(eps), True, want_exp)
             Fs.append(F)
             Es.append(expF)
         F = Fs[0] if len(Fs) == 1 else torch.cat(Fs, 0)

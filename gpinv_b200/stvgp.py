@@ -148,13 +148,17 @@ class StVGP(GPModel):
         want_exp = bool(getattr(self.likelihood, "wants_expF", False))
         Fs, Es, KLs = [], [], []
         for core, r0, r1 in chol.groups():
+            # (one group over all latent functions: no slices -- the reverse of a slice is a zero fill plus a copy,
+            #  eight extra launches per evaluation for the common single-kernel model)
+            def part(t, r0=r0, r1=r1):
+                return t if (r0 == 0 and r1 == t.shape[0]) else t[r0:r1]
             if chol.kron:
                 from . import kronecker
-                F, expF, KL = kronecker.kron_sample(core, chol.sqrt_var[r0:r1], Q[r0:r1], q_mu[r0:r1],
-                                                    mean[r0:r1], eps[r0:r1], self.q_diag, want_exp)
+                F, expF, KL = kronecker.kron_sample(core, part(chol.sqrt_var), part(Q), part(q_mu),
+                                                    part(mean), part(eps), self.q_diag, want_exp)
             else:
-                F, expF, KL, _ = ops.stvgp_sample(core, chol.sqrt_var[r0:r1].contiguous(), Q[r0:r1],
-                                                  q_mu[r0:r1], mean[r0:r1], eps[r0:r1],
+                F, expF, KL, _ = ops.stvgp_sample(core, part(chol.sqrt_var).contiguous(), part(Q),
+                                                  part(q_mu), part(mean), part(eps),
                                                   self.q_diag, want_exp)
             Fs.append(F)
             Es.append(expF)

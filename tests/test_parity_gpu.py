@@ -631,6 +631,41 @@ def test_cuda_graph_follows_data_and_fixed_parameter_changes():
     both()
 
 
+def test_cuda_graph_static_inputs_are_read_in_place():
+    """enable_cuda_graph(static_inputs=True): the graph reads the caller's x and eps tensors themselves (no copies
+    per replay); in-place updates of those tensors show up, and a different tensor gets its own capture."""
+    import torch
+    m = make_abel_stvgp(64, 50, 12)
+    m.kern.lengthscales = 0.3
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(4)
+    x0, x1 = perturbed_state(m, 0.05, seed=1), perturbed_state(m, 0.05, seed=2)
+    e0, e1 = rng.randn(1, 12, 64), rng.randn(1, 12, 64)
+    ref = {}
+    for k, (x, e) in {"00": (x0, e0), "10": (x1, e0), "11": (x1, e1)}.items():
+        f, g = m._objective(x, eps=e)
+        ref[k] = (float(f), np.array(g))
+    m.enable_cuda_graph(static_inputs=True)
+    xd, ed = torch.as_tensor(x0).to(dev), torch.as_tensor(e0).to(dev)
+
+    def run():
+        f, g = m._objective_device(xd, eps=ed)
+        return float(f.item()), g.cpu().numpy()
+
+    assert same_evaluation(*run(), *ref["00"], 4, f_tol=1e-11, q_tol=1e-11)
+    assert same_evaluation(*run(), *ref["00"], 4, f_tol=1e-11, q_tol=1e-11)
+    n_graphs = len(m._graphs)
+    xd.copy_(torch.as_tensor(x1))                           # in place: same capture, new values
+    assert same_evaluation(*run(), *ref["10"], 4, f_tol=1e-11, q_tol=1e-11)
+    ed.copy_(torch.as_tensor(e1))
+    assert same_evaluation(*run(), *ref["11"], 4, f_tol=1e-11, q_tol=1e-11)
+    assert len(m._graphs) == n_graphs
+    xd2 = torch.as_tensor(x0).to(dev)                       # another tensor: its own capture
+    f, g = m._objective_device(xd2, eps=torch.as_tensor(e0).to(dev))
+    assert same_evaluation(float(f.item()), g.cpu().numpy(), *ref["00"], 4, f_tol=1e-11, q_tol=1e-11)
+    assert len(m._graphs) == n_graphs + 1
+
+
 def test_dist_attach_refuses_models_without_samples():
     gpmc, kernels, kronecker, likelihoods, mean_functions, stvgp = _gp()
     from gpinv_b200 import dist as gdist
