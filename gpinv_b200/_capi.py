@@ -71,6 +71,10 @@ SIGNATURES = {
     "gpinv_kl_white_f64": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "gpinv_kl_white_bwd_f64": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "gpinv_adam_step_f64": (_I, [_P, _P, _P, _P, C.c_longlong, _D, _D, _D, _D, _P, _P]),
+    "gpinv_side_mark_inputs": (_I, [_P]),
+    "gpinv_side_early_join": (_I, [_P]),
+    "gpinv_sample_u_early_f64": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _I]),
+    "gpinv_sample_fwd2_f64": (_I, [_P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "gpinv_gauss_logp_f64": (_I, [_P, _P, _D, _P, _P]),
     "gpinv_gauss_logp_bwd_f64": (_I, [_P, _P, _D, _P, _P, _P, _P]),
     "gpinv_lbar_pack_f64": (_I, [_P, _I, _I, _I, _I, _P, _P]),

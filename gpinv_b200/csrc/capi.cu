@@ -49,6 +49,11 @@ int kbuild_bwd_ex_f64(const double*, const double*, int, int, int, int, int, con
 int tril_unpack_f64(const double*, double*, int, int, cudaStream_t);
 int tril_pack_f64(const double*, double*, int, int, cudaStream_t);
 int sumsq_f64(const double*, size_t, double*, cudaStream_t);
+int side_mark_inputs(cudaStream_t);
+int side_early_join(cudaStream_t);
+int sample_u_early_f64(const double*, int, const double*, const double*, int, int, int, double*, double*, int);
+int sample_fwd2_f64(const double*, int, const double*, const double*, int, const double*, const double*,
+                    const double*, int, int, int, double*, double*, double*, double*, int, cudaStream_t);
 int sample_fwd_f64(const double*, int, const double*, const double*, int, const double*,
                    const double*, const double*, int, int, int, double*, double*, double*, double*,
                    cudaStream_t);
@@ -333,6 +338,19 @@ int gpinv_sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const 
                          void* stream) {
   return sample_fwd_f64(Lc, ldl, sqrt_v, Q, q_diag, q_mu, mean, E, n, S, R, U, F, expF, kl_out,
                         ST(stream));
+}
+
+int gpinv_side_mark_inputs(void* stream) { return side_mark_inputs(ST(stream)); }
+int gpinv_side_early_join(void* stream) { return side_early_join(ST(stream)); }
+int gpinv_sample_u_early_f64(const double* Q, int q_diag, const double* q_mu, const double* E, int n, int S, int R,
+                             double* U, double* kl_out, int max_ctas) {
+  if (n <= 0 || S <= 0 || R <= 0 || !Q || !q_mu || !E || !U || !kl_out) return GPINV_ERR_ARG;
+  return sample_u_early_f64(Q, q_diag, q_mu, E, n, S, R, U, kl_out, max_ctas);
+}
+int gpinv_sample_fwd2_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q, int q_diag,
+                          const double* q_mu, const double* mean, const double* E, int n, int S, int R, double* U,
+                          double* F, double* expF, double* kl_out, int u_ready, void* stream) {
+  return sample_fwd2_f64(Lc, ldl, sqrt_v, Q, q_diag, q_mu, mean, E, n, S, R, U, F, expF, kl_out, u_ready, ST(stream));
 }
 
 int gpinv_sample_bwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q,

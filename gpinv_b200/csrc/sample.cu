@@ -283,8 +283,17 @@ int sumsq_f64(const double* x, size_t count, double* out, cudaStream_t st) {
 // U = q_mu + tril(Q) eps (GPinv/stvgp.py:162-168) and the partial sums of the stochastic KL
 // (GPinv/stvgp.py:160-161,170-172).  kl_out: device [4] = {KL, sumE2, sumU2, logdet}; KL itself is
 // written by kl_finish_f64 once sumU2 is complete.
+int sample_u_fwd_ex_f64(const double* Q, int q_diag, const double* q_mu, const double* E, int n, int S, int R,
+                        double* U, double* kl_out, int max_ctas, cudaStream_t st);
+
 int sample_u_fwd_f64(const double* Q, int q_diag, const double* q_mu, const double* E, int n, int S, int R,
                      double* U, double* kl_out, cudaStream_t st) {
+  return sample_u_fwd_ex_f64(Q, q_diag, q_mu, E, n, S, R, U, kl_out, 0, st);
+}
+
+// max_ctas > 0: the GEMM leaves SMs free (it runs beside the Cholesky factorisation, see sample_u_early_f64)
+int sample_u_fwd_ex_f64(const double* Q, int q_diag, const double* q_mu, const double* E, int n, int S, int R,
+                        double* U, double* kl_out, int max_ctas, cudaStream_t st) {
   GPINV_TRY(cudaMemsetAsync(kl_out, 0, 4 * sizeof(double), st));
   const size_t sn = (size_t)S * n;
   sumsq_kernel<<<ew_grid((size_t)R * sn / 2 + 1), 256, 0, st>>>(E, (size_t)R * sn, kl_out + 1);
@@ -307,10 +316,31 @@ int sample_u_fwd_f64(const double* Q, int q_diag, const double* q_mu, const doub
     p.out = U + r * sn; p.ldo = n;
     p.sumsq = kl_out + 2;
     p.kmode = 1; p.splitk = 1; p.allow_split = 1;
+    p.max_ctas = max_ctas;
     const int rc = gemm_launch(LK, LK, EF_COLVEC | EF_SUMSQ, p, st);
     if (rc) return rc;
   }
   return GPINV_OK;
+}
+
+// helpers of the library's stream set (potrf.cu)
+int side_early_begin(cudaStream_t* out);
+int side_early_end();
+int side_early_join(cudaStream_t st);
+
+// U = E tril(Q)^T + q_mu and the KL partial sums do not depend on the Cholesky factor: this entry runs them on
+// the library's low-priority stream, behind (a) the point marked with side_mark_inputs (their inputs exist)
+// and (b) the middle of the most recent factorisation (from there on its trailing updates no longer fill the
+// machine), so that the 0.5 ms product hides inside the factorisation's latency chain.  sample_fwd2_f64 with
+// u_ready = 1 joins it and continues with F = sqrt(v) U Lc^T + mean.
+int sample_u_early_f64(const double* Q, int q_diag, const double* q_mu, const double* E, int n, int S, int R,
+                       double* U, double* kl_out, int max_ctas) {
+  cudaStream_t s2 = nullptr;
+  int rc = side_early_begin(&s2);
+  if (rc) return rc;
+  rc = sample_u_fwd_ex_f64(Q, q_diag, q_mu, E, n, S, R, U, kl_out, max_ctas, s2);
+  if (rc) return rc;
+  return side_early_end();
 }
 
 int kl_finish_f64(double* kl_out, int S, cudaStream_t st) {
@@ -321,12 +351,23 @@ int kl_finish_f64(double* kl_out, int S, cudaStream_t st) {
 }
 
 // kl_out: device [4] = {KL, sumE2, sumU2, logdet}
+int sample_fwd2_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q, int q_diag,
+                    const double* q_mu, const double* mean, const double* E, int n, int S, int R,
+                    double* U, double* F, double* expF, double* kl_out, int u_ready, cudaStream_t st);
+
 int sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q, int q_diag,
                    const double* q_mu, const double* mean, const double* E, int n, int S, int R,
                    double* U, double* F, double* expF, double* kl_out, cudaStream_t st) {
+  return sample_fwd2_f64(Lc, ldl, sqrt_v, Q, q_diag, q_mu, mean, E, n, S, R, U, F, expF, kl_out, 0, st);
+}
+
+// u_ready: U and the partial sums in kl_out were produced by sample_u_early_f64
+int sample_fwd2_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q, int q_diag,
+                    const double* q_mu, const double* mean, const double* E, int n, int S, int R,
+                    double* U, double* F, double* expF, double* kl_out, int u_ready, cudaStream_t st) {
   if (n <= 0 || S <= 0 || R <= 0) return GPINV_ERR_ARG;
   if (!F && !expF) return GPINV_ERR_ARG;
-  int rc = sample_u_fwd_f64(Q, q_diag, q_mu, E, n, S, R, U, kl_out, st);
+  int rc = u_ready ? side_early_join(st) : sample_u_fwd_f64(Q, q_diag, q_mu, E, n, S, R, U, kl_out, st);
   if (rc) return rc;
   const size_t sn = (size_t)S * n;
   for (int r = 0; r < R; ++r) {

@@ -474,23 +474,53 @@ tril_unpack.register_autograd(lambda ctx, g: tril_pack(g.contiguous()), setup_co
 # --------------------------------------------------------------------------------------
 @torch.library.custom_op("gpinv::stvgp_sample", mutates_args=(), device_types="cuda")
 def stvgp_sample(Lc: Tensor, sqrt_v: Tensor, Q: Tensor, q_mu: Tensor, mean: Tensor, E: Tensor,
-                 q_diag: bool, want_exp: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                 q_diag: bool, want_exp: bool, U_pre: Optional[Tensor] = None,
+                 kl_pre: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """(F [R,S,n], expF [R,S,n] or empty, KL [1], U [R,S,n]).  GPinv/stvgp.py:144-185.
     Lc [n,n] lower core factor, sqrt_v [R], Q [R,n,n] lower (or [R,n] if q_diag), q_mu [R,n],
-    mean [R,n], E [R,S,n]."""
+    mean [R,n], E [R,S,n].  ``U_pre`` / ``kl_pre``: the first half of the stage was already run by
+    ``sample_u_early`` (beside the Cholesky factorisation); the U output is then empty and ``U_pre`` is what the
+    reverse pass uses."""
     Lc = _chk(Lc, "Lc"); sqrt_v = _chk(sqrt_v, "sqrt_v"); Q = _chk(Q, "Q")
     q_mu = _chk(q_mu, "q_mu"); mean = _chk(mean, "mean"); E = _chk(E, "E")
     ensure_workspace(E.device)
     R, S, n = E.shape
-    U = torch.empty_like(E)
+    lib = _capi.lib()
+    early = U_pre is not None and kl_pre is not None
+    if early:
+        _capi.check(lib.gpinv_side_early_join(_st()), "side_early_join")       # before kl_pre is read below
+        U = U_pre
+        kl = kl_pre.clone()
+    else:
+        U = torch.empty_like(E)
+        kl = torch.empty(4, dtype=torch.float64, device=E.device)
     F = torch.empty_like(E)
     expF = torch.empty_like(E) if want_exp else torch.empty(0, dtype=torch.float64, device=E.device)
-    kl = torch.empty(4, dtype=torch.float64, device=E.device)
-    rc = _capi.lib().gpinv_sample_fwd_f64(_p(Lc), n, _p(sqrt_v), _p(Q), int(q_diag), _p(q_mu),
-                                          _p(mean), _p(E), n, S, R, _p(U), _p(F),
-                                          _p(expF) if want_exp else None, _p(kl), _st())
+    rc = lib.gpinv_sample_fwd2_f64(_p(Lc), n, _p(sqrt_v), _p(Q), int(q_diag), _p(q_mu),
+                                   _p(mean), _p(E), n, S, R, _p(U), _p(F),
+                                   _p(expF) if want_exp else None, _p(kl), 1 if early else 0, _st())
     _capi.check(rc, "sample_fwd")
-    return F, expF, kl[:1].clone(), U
+    return F, expF, kl[:1].clone(), (torch.empty(0, dtype=torch.float64, device=E.device) if early else U)
+
+
+def mark_inputs_ready() -> None:
+    """Mark the point of the current stream where the inputs of ``sample_u_early`` exist (call before chol_core)."""
+    _capi.check(_capi.lib().gpinv_side_mark_inputs(_st()), "side_mark_inputs")
+
+
+def sample_u_early(Q: Tensor, q_mu: Tensor, E: Tensor, q_diag: bool, U: Tensor, kl: Tensor, max_ctas: int = 0) -> None:
+    """U [R,S,n] <- E tril(Q)^T + q_mu and kl [4] <- the KL partial sums, on the library's low-priority stream,
+    behind ``mark_inputs_ready`` and the middle of the most recent Cholesky factorisation; no autograd -- the
+    results are handed to ``stvgp_sample`` (U_pre, kl_pre), whose reverse pass is unchanged.  U and kl are
+    allocated by the caller BEFORE ``mark_inputs_ready`` (nothing enqueued later may still own their memory)."""
+    import os
+    Q = _chk(Q, "Q"); q_mu = _chk(q_mu, "q_mu"); E = _chk(E, "E")
+    ensure_workspace(E.device)
+    R, S, n = E.shape
+    if max_ctas <= 0:
+        max_ctas = int(os.environ.get("GPINV_EARLY_U_CAP", "100"))
+    rc = _capi.lib().gpinv_sample_u_early_f64(_p(Q), int(q_diag), _p(q_mu), _p(E), n, S, R, _p(U), _p(kl), int(max_ctas))
+    _capi.check(rc, "sample_u_early")
 
 
 @torch.library.custom_op("gpinv::stvgp_sample_bwd", mutates_args=(), device_types="cuda")
@@ -518,8 +548,10 @@ def stvgp_sample_bwd(Lc: Tensor, sqrt_v: Tensor, Q: Tensor, E: Tensor, U: Tensor
 
 
 def _sample_setup(ctx, inputs, output):
-    Lc, sqrt_v, Q, q_mu, mean, E, q_diag, want_exp = inputs
+    Lc, sqrt_v, Q, q_mu, mean, E, q_diag, want_exp, U_pre, _kl_pre = inputs
     F, expF, kl, U = output
+    if U_pre is not None:
+        U = U_pre
     ctx.save_for_backward(Lc, sqrt_v, Q, E, U, expF)
     ctx.q_diag = q_diag
     ctx.want_exp = want_exp
@@ -537,7 +569,7 @@ def _sample_backward(ctx, Fbar, expFbar, klbar, Ubar_unused):
         ctx.q_diag)
     # Qbar's strict upper triangle is unspecified; tril_unpack's backward masks it.  For the
     # q_diag layout Qbar is exact.
-    return Lc_bar, sv_bar, Qbar, qmu_bar, mean_bar, None, None, None
+    return Lc_bar, sv_bar, Qbar, qmu_bar, mean_bar, None, None, None, None, None
 
 
 stvgp_sample.register_autograd(_sample_backward, setup_context=_sample_setup)

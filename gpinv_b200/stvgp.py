@@ -137,14 +137,26 @@ class StVGP(GPModel):
         """f = mean + L (q_mu + tril(q_sqrt) eps) for every draw; stores the stochastic KL in
         ``self._KL`` (GPinv/stvgp.py:144-185).  Returns ([S,n,R] views of) F and exp(F)."""
         R = self.num_latent
-        chol = self.kern.Cholesky_factor(self.X)
+        U_pre = kl_pre = None
+        if self._early_u_applies(eps):
+            # u = q_mu + tril(q_sqrt) eps does not depend on the Cholesky factor: prepare its operands first, and
+            # run it on a low-priority stream from the middle of the factorisation on (ops.sample_u_early)
+            q_mu = self.q_mu.T.contiguous()
+            Q = ops.tril_unpack(self.q_sqrt)
+            U_pre = torch.empty_like(eps)
+            kl_pre = torch.empty(4, dtype=torch.float64, device=eps.device)
+            ops.mark_inputs_ready()
+            chol = self.kern.Cholesky_factor(self.X)
+            ops.sample_u_early(Q.detach(), q_mu.detach(), eps, False, U_pre, kl_pre)
+        else:
+            chol = self.kern.Cholesky_factor(self.X)
+            q_mu = self.q_mu.T.contiguous()                        # [R,n]
+            if self.q_diag:
+                Q = self.q_sqrt.T.contiguous()                     # [R,n]
+            else:
+                Q = ops.tril_unpack(self.q_sqrt)                   # [R,n,n], zeros above diag
         self._pending_infos += chol.infos
         mean = self.mean_function(self.X).T.contiguous()          # [R,n]
-        q_mu = self.q_mu.T.contiguous()                            # [R,n]
-        if self.q_diag:
-            Q = self.q_sqrt.T.contiguous()                         # [R,n]
-        else:
-            Q = ops.tril_unpack(self.q_sqrt)                       # [R,n,n], zeros above diag
         want_exp = bool(getattr(self.likelihood, "wants_expF", False))
         Fs, Es, KLs = [], [], []
         for core, r0, r1 in chol.groups():
@@ -159,7 +171,7 @@ class StVGP(GPModel):
             else:
                 F, expF, KL, _ = ops.stvgp_sample(core, part(chol.sqrt_var).contiguous(), part(Q),
                                                   part(q_mu), part(mean), part(eps),
-                                                  self.q_diag, want_exp)
+                                                  self.q_diag, want_exp, U_pre, kl_pre)
             Fs.append(F)
             Es.append(expF)
             KLs.append(KL)
@@ -172,6 +184,25 @@ class StVGP(GPModel):
             KL = KL + k
         self._KL = KL
         return F.permute(1, 2, 0), expF
+
+    EARLY_U_MIN_N = 2048          # factor size from which the first sampling product is hidden in the factorisation
+    EARLY_U_MIN_WORK = 1 << 32    # ... and the minimum S n^2 of that product
+
+    def _early_u_applies(self, eps):
+        """One latent function, one plain stationary kernel (one factorisation, no Kronecker structure), a full
+        q_sqrt that is already on the device (not the pending upload of the pipelined host path)."""
+        import os
+        from . import kernels
+        if os.environ.get("GPINV_EARLY_U", "1") == "0" or self.q_diag or self.num_latent != 1:
+            return False
+        if self.dist is not None and self.dist.world_size > 1:
+            return False          # (per-rank product is S/G rows: little to hide; not validated under sharding)
+        n = self.num_data
+        if n < self.EARLY_U_MIN_N or eps.shape[1] * n * n < self.EARLY_U_MIN_WORK:
+            return False
+        if type(self.kern) not in (kernels.RBF, kernels.RBF_csym, kernels.RBF_casym):
+            return False
+        return object.__getattribute__(self, "q_sqrt")._before_use is None
 
     def _analytical_KL(self):
         """GPinv/stvgp.py:187-195 -> GPflow gauss_kl_white[_diag]; one reduction kernel over q_mu and the

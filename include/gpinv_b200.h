@@ -149,6 +149,19 @@ int gpinv_sample_fwd_f64(const double* Lc, int ldl, const double* sqrt_v, const 
                          int q_diag, const double* q_mu, const double* mean, const double* E,
                          int n, int S, int R, double* U, double* F, double* expF, double* kl_out,
                          void* stream);
+/* The first half of that stage, u = q_mu + tril(q_sqrt) eps and the KL partial sums (GPinv/stvgp.py:162-172), does
+ * not depend on the Cholesky factor of GPinv/kernels.py:59.  gpinv_side_mark_inputs marks the point of `stream`
+ * where its inputs exist (call it BEFORE gpinv_chol_core_*); gpinv_sample_u_early_f64 (call it AFTER) runs that
+ * half, CTA-capped, on a low-priority stream of the library, behind the marked point and the middle of the most
+ * recent factorisation -- the product hides inside the factorisation's latency chain; gpinv_sample_fwd2_f64
+ * with u_ready = 1 waits for it (gpinv_side_early_join) and continues with f = sqrt(v) Lc u + mean.  n > 512. */
+int gpinv_side_mark_inputs(void* stream);
+int gpinv_side_early_join(void* stream);
+int gpinv_sample_u_early_f64(const double* Q, int q_diag, const double* q_mu, const double* E, int n, int S, int R,
+                             double* U, double* kl_out, int max_ctas);
+int gpinv_sample_fwd2_f64(const double* Lc, int ldl, const double* sqrt_v, const double* Q, int q_diag,
+                          const double* q_mu, const double* mean, const double* E, int n, int S, int R, double* U,
+                          double* F, double* expF, double* kl_out, int u_ready, void* stream);
 /* reverse.  Fbar [R,S,n] = dObj/dF, klbar device scalar dObj/dKL (NULL = 0).
  * Outputs: Ubar [R,S,n]; qmu_bar [R,n]; Qbar [R,n,n] lower (or [R,n]); Lc_bar [n,n] lower
  * (summed over r); svdot [R] = sv_r <tril(Fbar_r^T U_r), Lc>; mean_bar [R,n]. */
