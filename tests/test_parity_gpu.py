@@ -631,6 +631,33 @@ def test_cuda_graph_follows_data_and_fixed_parameter_changes():
     both()
 
 
+def test_early_sampling_product_matches_plain_order(monkeypatch):
+    """n >= 2048 on the device path: U = E tril(Q)^T + q_mu is issued on the library's low-priority stream from the
+    middle of the Cholesky factorisation on (ops.sample_u_early).  Same evaluation as with the plain order
+    (GPINV_EARLY_U=0), eager and replayed, for a state that changes between calls."""
+    import torch
+    n, M, S = 2048, 96, 1024
+    m = make_abel_stvgp(n, M, S)
+    m.kern.lengthscales = 0.3
+    dev = torch.device("cuda:0")
+    eps = torch.randn((1, S, n), dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    xs = [torch.as_tensor(perturbed_state(m, 0.02, seed=s)).to(dev) for s in (1, 2)]
+    assert m._early_u_applies(eps)
+    monkeypatch.setenv("GPINV_EARLY_U", "0")
+    assert not m._early_u_applies(eps)
+    plain = []
+    for x in xs:
+        f, g = m._objective_device(x, eps=eps)
+        plain.append((float(f.item()), g.cpu().numpy()))
+    monkeypatch.setenv("GPINV_EARLY_U", "1")
+    for graph in (False, True):
+        m.enable_cuda_graph(graph)
+        for rep in range(2):
+            for x, (f0, g0) in zip(xs, plain):
+                f, g = m._objective_device(x, eps=eps)
+                assert same_evaluation(float(f.item()), g.cpu().numpy(), f0, g0, 4, hyper_tol=1e-6), (graph, rep)
+
+
 def test_cuda_graph_static_inputs_are_read_in_place():
     """enable_cuda_graph(static_inputs=True): the graph reads the caller's x and eps tensors themselves (no copies
     per replay); in-place updates of those tensors show up, and a different tensor gets its own capture."""
